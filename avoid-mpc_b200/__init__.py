@@ -1,0 +1,4 @@
+"""avoid-mpc_b200: B200-native batched collision-avoidance MPC hot path
+(k-NN over depth clouds + quadrotor NLP solve) behind the call surface of
+SJTU-ViSYS-team/Avoid-MPC.  See DESIGN.md."""
+from . import defaults, synth  # noqa: F401
