@@ -1,0 +1,794 @@
+// libampc.so — C-ABI (include/ampc.h) over the sm_100a kernels.
+// No torch types, no CPU fallback: every compute entry point launches CUDA
+// kernels and returns AMPC_ERR_CUDA (with text in ampc_last_error) if it cannot.
+#include "../../include/ampc.h"
+
+#include "common.cuh"
+#include "ipm_solve.cuh"
+#include "knn_scan.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace ampc;
+
+static_assert(sizeof(ampc_solve_info) == sizeof(SolveOut), "ampc_solve_info layout");
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_create_mutex;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= bytes)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess)
+            bytes = n;
+        return e;
+    }
+    void release() {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+} // namespace
+
+struct ampc_handle {
+    ampc_config cfg{};
+    ampc_solver_opts opts{};
+    double weights[25], tau[4], gains[4], radius;
+    double lb[4], ub[4];
+    SolveConsts consts{};
+    bool consts_dirty = true;
+    int n_w = 0, n_prefix = 0;
+    cudaStream_t stream = nullptr;
+    // clouds: [kind] slot buffers + counts
+    DevBuf cloud[2], counts[2];
+    int slot_points[2] = {0, 0};
+    DevBuf raw_stage; // staging for stride != 16 uploads
+    // batch workspaces
+    DevBuf queries, prefix, w, info, knn_idx, knn_d2, knn_cnt, knn_pts, scene_of, x0, ref, posx, replan;
+    DevBuf ws_d, ws_i, ws_counter;
+    DevBuf bo_arg, bo_cost;
+    int64_t launches = 0;
+    std::string err;
+    int solve_smem_set = 0;
+    int knn_smem_set = 0;
+};
+
+namespace {
+
+int fail(ampc_handle *h, int code, const std::string &msg) {
+    if (h)
+        h->err = msg;
+    return code;
+}
+int cuda_fail(ampc_handle *h, cudaError_t e, const char *what) {
+    return fail(h, AMPC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return cuda_fail(h, e__, #call);                                                       \
+    } while (0)
+
+// ---- discrete dynamics: 4 RK4 sub-steps of dt/4 of the affine ODE
+// (tools/mpc_obstacle_casadi.py:106-122,338-357); F is affine, so Phi/Gam/gam are
+// read off F applied to unit vectors (the RK4 polynomial, not expm).
+void ode_rhs(const double *x, const double *u, const double *tau, double *xd) {
+    xd[0] = x[4], xd[1] = x[5], xd[2] = x[6];
+    xd[3] = u[3];
+    xd[4] = x[7], xd[5] = x[8], xd[6] = x[9];
+    xd[7] = (u[0] - x[7]) * tau[0];
+    xd[8] = (u[1] - x[8]) * tau[1];
+    xd[9] = (u[2] - 9.81 - x[9]) * tau[2];
+}
+void rk4_map(const double *x0, const double *u, const double *tau, double dt, double *xn) {
+    const double h = dt / 4;
+    double X[10], k1[10], k2[10], k3[10], k4[10], t[10];
+    std::memcpy(X, x0, sizeof X);
+    for (int m = 0; m < 4; ++m) {
+        ode_rhs(X, u, tau, k1);
+        for (int i = 0; i < 10; ++i) t[i] = X[i] + 0.5 * (k1[i] *= h);
+        ode_rhs(t, u, tau, k2);
+        for (int i = 0; i < 10; ++i) t[i] = X[i] + 0.5 * (k2[i] *= h);
+        ode_rhs(t, u, tau, k3);
+        for (int i = 0; i < 10; ++i) t[i] = X[i] + (k3[i] *= h);
+        ode_rhs(t, u, tau, k4);
+        for (int i = 0; i < 10; ++i) X[i] = X[i] + (k1[i] + 2 * k2[i] + 2 * k3[i] + (k4[i] *= h)) / 6;
+    }
+    std::memcpy(xn, X, sizeof X);
+}
+void refresh_consts(ampc_handle *h) {
+    if (!h->consts_dirty)
+        return;
+    SolveConsts &c = h->consts;
+    double z[10] = {0}, zu[4] = {0}, col[10];
+    rk4_map(z, zu, h->tau, h->cfg.dt, c.gam);
+    for (int j = 0; j < 10; ++j) {
+        double e[10] = {0};
+        e[j] = 1.0;
+        rk4_map(e, zu, h->tau, h->cfg.dt, col);
+        for (int i = 0; i < 10; ++i) c.Phi[i * 10 + j] = col[i] - c.gam[i];
+    }
+    for (int j = 0; j < 4; ++j) {
+        double e[4] = {0};
+        e[j] = 1.0;
+        rk4_map(z, e, h->tau, h->cfg.dt, col);
+        for (int i = 0; i < 10; ++i) c.Gam[i * 4 + j] = col[i] - c.gam[i];
+    }
+    std::memcpy(c.wgt, h->weights, sizeof c.wgt);
+    c.radius = h->radius;
+    std::memcpy(c.lb, h->lb, sizeof c.lb);
+    std::memcpy(c.ub, h->ub, sizeof c.ub);
+    c.tol = h->opts.tol;
+    c.mu_init = h->opts.mu_init;
+    c.bound_push = h->opts.bound_push;
+    c.bound_frac = h->opts.bound_frac;
+    c.eps_min = h->opts.eps_min;
+    c.eps_scale = h->opts.eps_scale;
+    c.max_iter = h->opts.max_iter;
+    c.N = h->cfg.N;
+    c.K = h->cfg.K;
+    c.n_prefix = h->n_prefix;
+    h->consts_dirty = false;
+}
+
+// ---- small kernels around the two hot ones --------------------------------
+
+// stride != 16 uploads: repack raw records into float4 slots
+__global__ void repack_kernel(const unsigned char *raw, int64_t scene_stride, int stride,
+                              float4 *clouds, const int32_t *counts, int64_t slot_points,
+                              int first_scene) {
+    const int scene = first_scene + blockIdx.y;
+    const int n = counts[scene];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float *p = reinterpret_cast<const float *>(raw + (int64_t)blockIdx.y * scene_stride +
+                                                         (int64_t)i * stride);
+        clouds[(int64_t)scene * slot_points + i] = make_float4(p[0], p[1], p[2], 1.0f);
+    }
+}
+
+// GetRefStates (src/AvoidanceStateMachine.cpp:236-257) minus the obstacle block
+// (written by the k-NN kernel), plus the Q = N query sites of ProcessWaypoints
+// (:211-215).  One thread per (instance, element).
+__global__ void pack_prefix_kernel(int B, int N, int K, const double *x0, const double *ref,
+                                   const double *pos_x, double speed, double T, double *prefix,
+                                   int n_prefix, double *queries) {
+    const int b = blockIdx.x;
+    if (b >= B)
+        return;
+    double *p = prefix + (int64_t)b * n_prefix;
+    const double *r = ref + (int64_t)b * N * 10;
+    for (int i = threadIdx.x; i < 10; i += blockDim.x)
+        p[i] = x0[(int64_t)b * 10 + i];
+    for (int i = threadIdx.x; i < 10 * N; i += blockDim.x)
+        p[10 + i] = r[i];
+    for (int i = threadIdx.x; i < 3 * N; i += blockDim.x) {
+        const int k = i / 3, c = i - 3 * k;
+        queries[(int64_t)b * 3 * N + i] = r[10 * k + c];
+    }
+    if (threadIdx.x < 10) { // target rule, :250-255
+        const int i = threadIdx.x;
+        double v = r[10 * (N - 1) + i];
+        if (i == 0) {
+            const double px = pos_x ? pos_x[b] : x0[(int64_t)b * 10];
+            double dX = speed * T - fmax(0.0, v - px);
+            dX = fmax(0.0, dX);
+            v += dX;
+        }
+        if (i == 1)
+            v = 0.0;
+        p[10 + 10 * N + 3 * K * N + i] = v;
+    }
+}
+
+// needReplan of ProcessWaypoints (:228-231)
+__global__ void replan_kernel(int B, int Q, int k, const double *dist2, const int32_t *count,
+                              double safety, int32_t *need_replan) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B)
+        return;
+    int flag = 0;
+    for (int q = 0; q < Q; ++q) {
+        const int c = count[(int64_t)b * Q + q];
+        if (c == 0 || sqrt(dist2[((int64_t)b * Q + q) * k]) <= safety)
+            flag = 1;
+    }
+    need_replan[b] = flag;
+}
+
+__global__ void best_of_kernel(int n_scenes, int G, const SolveOut *info, int32_t *argmin,
+                               double *best) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scenes)
+        return;
+    int a = -1;
+    double c = INFINITY;
+    for (int g = 0; g < G; ++g) {
+        const SolveOut &o = info[(int64_t)s * G + g];
+        if ((o.status == AMPC_SOLVE_CONVERGED || o.status == AMPC_SOLVE_MAX_ITER) && o.cost < c) {
+            c = o.cost;
+            a = g;
+        }
+    }
+    argmin[s] = a;
+    best[s] = c;
+}
+
+int check_kind(ampc_handle *h, int kind) {
+    if (kind != AMPC_CLOUD_OBSTACLE && kind != AMPC_CLOUD_EDGE)
+        return fail(h, AMPC_ERR_INVALID, "kind must be AMPC_CLOUD_OBSTACLE or AMPC_CLOUD_EDGE");
+    if (h->slot_points[kind] <= 0)
+        return fail(h, AMPC_ERR_CAPACITY, "handle was created without capacity for this cloud kind");
+    return AMPC_OK;
+}
+
+int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, const double *q_dev,
+               int Q, int k, int32_t *idx, double *d2, int32_t *cnt, double *pts, int64_t pts_is,
+               int64_t pts_qs, cudaStream_t st) {
+    if (k < 1 || k > KNN_KMAX)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "k must be in 1..32");
+    if (Q < 1 || B < 1)
+        return fail(h, AMPC_ERR_INVALID, "B and Q must be positive");
+    const size_t smem = knn_smem_bytes(Q, k);
+    if (smem > 200 * 1024)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "Q*k too large for the shared-memory top-k lists");
+    if ((int)smem > h->knn_smem_set) {
+        CK(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->knn_smem_set = (int)smem;
+    }
+    // segments: enough CTAs to fill 148 SMs when the batch is small
+    int segs = 1;
+    const int target_ctas = 148 * 4;
+    if (B < target_ctas) {
+        const int max_useful = (h->slot_points[kind] + KNN_WARPS * KNN_TILE * 4 - 1) / (KNN_WARPS * KNN_TILE * 4);
+        segs = (target_ctas + B - 1) / B;
+        if (segs > max_useful)
+            segs = max_useful;
+        if (segs < 1)
+            segs = 1;
+    }
+    KnnParams P{};
+    P.clouds = h->cloud[kind].as<float4>();
+    P.counts = h->counts[kind].as<int32_t>();
+    P.slot_points = h->slot_points[kind];
+    P.scene_of = scene_of_dev;
+    P.queries = q_dev;
+    P.Q = Q;
+    P.k = k;
+    P.segs = segs;
+    P.idx = idx;
+    P.dist2 = d2;
+    P.count = cnt;
+    P.pts = pts;
+    P.pts_inst_stride = pts_is;
+    P.pts_query_stride = pts_qs;
+    if (segs > 1) {
+        const size_t n = (size_t)B * segs * Q * k;
+        CK(h->ws_d.reserve(n * 8));
+        CK(h->ws_i.reserve(n * 4));
+        if (h->ws_counter.bytes < (size_t)B * 4) {
+            CK(h->ws_counter.reserve((size_t)B * 4));
+            CK(cudaMemsetAsync(h->ws_counter.p, 0, h->ws_counter.bytes, st));
+        }
+        P.ws_d = h->ws_d.as<double>();
+        P.ws_i = h->ws_i.as<uint32_t>();
+        P.ws_counter = h->ws_counter.as<unsigned int>();
+    }
+    knn_scan_kernel<<<dim3(segs, B), KNN_THREADS, smem, st>>>(P);
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
+
+constexpr int SOLVE_WARPS = 2;
+
+int launch_solve(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
+                 cudaStream_t st) {
+    refresh_consts(h);
+    const size_t smem = solve_smem_bytes(h->cfg.N, SOLVE_WARPS);
+    if (smem > 227 * 1024)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "horizon too long for the per-warp shared-memory layout");
+    if ((int)smem > h->solve_smem_set) {
+        CK(cudaFuncSetAttribute(ipm_solve_kernel<SOLVE_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->solve_smem_set = (int)smem;
+    }
+    const int grid = (B + SOLVE_WARPS - 1) / SOLVE_WARPS;
+    ipm_solve_kernel<SOLVE_WARPS><<<grid, SOLVE_WARPS * 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev);
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
+
+int check_batch(ampc_handle *h, int B) {
+    if (!h)
+        return AMPC_ERR_INVALID;
+    if (B < 1)
+        return fail(h, AMPC_ERR_INVALID, "B must be positive");
+    if (B > h->cfg.max_batch)
+        return fail(h, AMPC_ERR_CAPACITY, "B exceeds ampc_config.max_batch");
+    return AMPC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int ampc_api_version(void) { return AMPC_API_VERSION; }
+
+const char *ampc_last_error(const ampc_handle *h) {
+    if (h)
+        return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_create_mutex);
+    return g_create_error.c_str();
+}
+
+void ampc_default_solver_opts(ampc_solver_opts *o) {
+    if (!o)
+        return;
+    o->tol = 1e-8;
+    o->max_iter = 100;
+    o->mu_init = 0.1;
+    o->bound_push = 1e-2;
+    o->bound_frac = 1e-2;
+    o->eps_min = 1e-5;
+    o->eps_scale = 1.0;
+}
+
+int ampc_create(const ampc_config *cfg, ampc_handle **out) {
+    auto cfail = [](int code, const std::string &m) {
+        std::lock_guard<std::mutex> g(g_create_mutex);
+        g_create_error = m;
+        return code;
+    };
+    if (!cfg || !out)
+        return cfail(AMPC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->N < 1 || cfg->N > 256 || cfg->K < 0 || cfg->K > KNN_KMAX || !(cfg->dt > 0) ||
+        cfg->max_batch < 1 || cfg->max_scenes < 0 || cfg->max_points < 0 || cfg->max_edge_points < 0)
+        return cfail(AMPC_ERR_INVALID, "bad ampc_config (need 1<=N<=256, 0<=K<=32, dt>0, max_batch>=1)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return cfail(AMPC_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                        " (libampc has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return cfail(AMPC_ERR_INVALID, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess)
+        return cfail(AMPC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    ampc_handle *h = new (std::nothrow) ampc_handle();
+    if (!h)
+        return cfail(AMPC_ERR_INVALID, "out of host memory");
+    h->cfg = *cfg;
+    h->n_w = 10 + 14 * cfg->N;
+    h->n_prefix = 20 + 10 * cfg->N + 3 * cfg->K * cfg->N;
+    ampc_default_solver_opts(&h->opts);
+    // defaults of the reference constructor (src/HighLvlMpc.cpp:11-14,53-58)
+    const double w0[25] = {100, 100, 100, 300, 1, 1, 1, 0., 0., 0., 0.0, 10, 10,
+                           30,  0,   1,   1,   0., 0., 0., 1., 1., 1., 1., 1.};
+    std::memcpy(h->weights, w0, sizeof w0);
+    const double t0[4] = {0.01, 0.01, 0.01, 0}, g0[4] = {1, 1, 1, 1};
+    std::memcpy(h->tau, t0, sizeof t0);
+    std::memcpy(h->gains, g0, sizeof g0);
+    h->radius = 0.0;
+    const double l0[4] = {-10., -10., 1., -10.}, u0[4] = {10., 10., 20., 10.};
+    std::memcpy(h->lb, l0, sizeof l0);
+    std::memcpy(h->ub, u0, sizeof u0);
+    auto bail = [&](cudaError_t ce, const char *what) {
+        std::string m = std::string(what) + ": " + cudaGetErrorString(ce);
+        ampc_destroy(h);
+        return cfail(AMPC_ERR_CUDA, m);
+    };
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(e, "cudaStreamCreate");
+    h->slot_points[0] = cfg->max_points;
+    h->slot_points[1] = cfg->max_edge_points;
+    for (int kind = 0; kind < 2; ++kind) {
+        if (cfg->max_scenes == 0 || h->slot_points[kind] == 0)
+            continue;
+        if ((e = h->cloud[kind].reserve((size_t)cfg->max_scenes * h->slot_points[kind] * 16)) != cudaSuccess)
+            return bail(e, "cudaMalloc(clouds)");
+        if ((e = h->counts[kind].reserve((size_t)cfg->max_scenes * 4)) != cudaSuccess)
+            return bail(e, "cudaMalloc(counts)");
+        if ((e = cudaMemset(h->counts[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
+            return bail(e, "cudaMemset(counts)");
+    }
+    const size_t B = (size_t)cfg->max_batch, N = (size_t)cfg->N, K = (size_t)(cfg->K > 0 ? cfg->K : 1);
+    struct { DevBuf *b; size_t n; } need[] = {
+        {&h->queries, B * N * 3 * 8}, {&h->prefix, B * (size_t)h->n_prefix * 8},
+        {&h->w, B * (size_t)h->n_w * 8}, {&h->info, B * sizeof(SolveOut)},
+        {&h->knn_idx, B * N * K * 4}, {&h->knn_d2, B * N * K * 8}, {&h->knn_cnt, B * N * 4},
+        {&h->scene_of, B * 4}, {&h->x0, B * 10 * 8}, {&h->ref, B * N * 10 * 8},
+        {&h->posx, B * 8}, {&h->replan, B * 4}, {&h->bo_arg, B * 4}, {&h->bo_cost, B * 8}};
+    for (auto &nb : need)
+        if ((e = nb.b->reserve(nb.n)) != cudaSuccess)
+            return bail(e, "cudaMalloc(workspace)");
+    *out = h;
+    return AMPC_OK;
+}
+
+void ampc_destroy(ampc_handle *h) {
+    if (!h)
+        return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream)
+        cudaStreamSynchronize(h->stream);
+    DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->raw_stage,
+                     &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
+                     &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
+                     &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost};
+    for (DevBuf *b : all)
+        b->release();
+    if (h->stream)
+        cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int ampc_set_weights(ampc_handle *h, const double w[25]) {
+    if (!h || !w) return AMPC_ERR_INVALID;
+    std::memcpy(h->weights, w, sizeof h->weights);
+    h->consts_dirty = true;
+    return AMPC_OK;
+}
+int ampc_set_tau(ampc_handle *h, const double t[4]) {
+    if (!h || !t) return AMPC_ERR_INVALID;
+    std::memcpy(h->tau, t, sizeof h->tau);
+    h->consts_dirty = true;
+    return AMPC_OK;
+}
+int ampc_set_gains(ampc_handle *h, const double g[4]) {
+    if (!h || !g) return AMPC_ERR_INVALID;
+    std::memcpy(h->gains, g, sizeof h->gains);
+    return AMPC_OK;
+}
+int ampc_set_radius(ampc_handle *h, double r) {
+    if (!h) return AMPC_ERR_INVALID;
+    h->radius = r;
+    h->consts_dirty = true;
+    return AMPC_OK;
+}
+int ampc_set_accel_limits(ampc_handle *h, double a_min_z, double a_max_z, double a_max_xy,
+                          double a_max_yaw_dot) {
+    if (!h) return AMPC_ERR_INVALID;
+    if (!(a_min_z < a_max_z) || !(a_max_xy > 0) || !(a_max_yaw_dot > 0))
+        return fail(h, AMPC_ERR_INVALID, "empty control box");
+    const double l[4] = {-a_max_xy, -a_max_xy, a_min_z, -a_max_yaw_dot};
+    const double u[4] = {a_max_xy, a_max_xy, a_max_z, a_max_yaw_dot};
+    std::memcpy(h->lb, l, sizeof l);
+    std::memcpy(h->ub, u, sizeof u);
+    h->consts_dirty = true;
+    return AMPC_OK;
+}
+int ampc_set_solver_opts(ampc_handle *h, const ampc_solver_opts *o) {
+    if (!h || !o) return AMPC_ERR_INVALID;
+    if (!(o->tol > 0) || o->max_iter < 0 || !(o->mu_init > 0) || !(o->eps_min >= 0))
+        return fail(h, AMPC_ERR_INVALID, "bad solver options");
+    h->opts = *o;
+    h->consts_dirty = true;
+    return AMPC_OK;
+}
+int ampc_get_dynamics(ampc_handle *h, double Phi[100], double Gam[40], double gam[10]) {
+    if (!h || !Phi || !Gam || !gam) return AMPC_ERR_INVALID;
+    refresh_consts(h);
+    std::memcpy(Phi, h->consts.Phi, sizeof h->consts.Phi);
+    std::memcpy(Gam, h->consts.Gam, sizeof h->consts.Gam);
+    std::memcpy(gam, h->consts.gam, sizeof h->consts.gam);
+    return AMPC_OK;
+}
+
+int64_t ampc_launch_count(const ampc_handle *h) { return h ? h->launches : 0; }
+void *ampc_stream(ampc_handle *h) { return h ? (void *)h->stream : nullptr; }
+int ampc_synchronize(ampc_handle *h) {
+    if (!h) return AMPC_ERR_INVALID;
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPC_OK;
+}
+
+// ---- clouds -----------------------------------------------------------------
+static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_scenes, const void *src,
+                            bool src_is_device, const int32_t *counts, int64_t scene_stride,
+                            int stride, cudaStream_t st) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, kind);
+    if (rc) return rc;
+    if (n_scenes < 1 || first_scene < 0 || first_scene + n_scenes > h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "scene range exceeds ampc_config.max_scenes");
+    if (!counts || (!src && n_scenes > 0))
+        return fail(h, AMPC_ERR_INVALID, "null cloud pointer");
+    if (stride < 12 || (stride & 3))
+        return fail(h, AMPC_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
+    int maxc = 0;
+    for (int s = 0; s < n_scenes; ++s) {
+        if (counts[s] < 0 || counts[s] > h->slot_points[kind])
+            return fail(h, AMPC_ERR_CAPACITY, "cloud has more points than the slot capacity");
+        if (counts[s] > maxc) maxc = counts[s];
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    int32_t *dcounts = h->counts[kind].as<int32_t>() + first_scene;
+    CK(cudaMemcpyAsync(dcounts, counts, (size_t)n_scenes * 4, cudaMemcpyHostToDevice, st));
+    float4 *slots = h->cloud[kind].as<float4>();
+    const int64_t slot_bytes = (int64_t)h->slot_points[kind] * 16;
+    const cudaMemcpyKind dir = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (maxc > 0) {
+        if (stride == 16) {
+            char *dst = reinterpret_cast<char *>(slots) + (int64_t)first_scene * slot_bytes;
+            if (n_scenes == 1 || (scene_stride == slot_bytes && maxc == h->slot_points[kind])) {
+                const size_t bytes = n_scenes == 1 ? (size_t)maxc * 16 : (size_t)n_scenes * slot_bytes;
+                CK(cudaMemcpyAsync(dst, src, bytes, dir, st));
+            } else {
+                if (scene_stride < (int64_t)maxc * 16)
+                    return fail(h, AMPC_ERR_INVALID, "scene_stride_bytes smaller than the largest cloud");
+                CK(cudaMemcpy2DAsync(dst, (size_t)slot_bytes, src, (size_t)scene_stride, (size_t)maxc * 16,
+                                     (size_t)n_scenes, dir, st));
+            }
+        } else {
+            if (n_scenes > 1 && scene_stride < (int64_t)maxc * stride)
+                return fail(h, AMPC_ERR_INVALID, "scene_stride_bytes smaller than the largest cloud");
+            const unsigned char *raw = static_cast<const unsigned char *>(src);
+            if (!src_is_device) {
+                const size_t per = n_scenes == 1 ? (size_t)maxc * stride : (size_t)scene_stride;
+                CK(h->raw_stage.reserve(per * n_scenes));
+                CK(cudaMemcpyAsync(h->raw_stage.p, src, per * n_scenes, cudaMemcpyHostToDevice, st));
+                raw = h->raw_stage.as<unsigned char>();
+                if (n_scenes == 1) scene_stride = (int64_t)per;
+            }
+            repack_kernel<<<dim3((maxc + 255) / 256 > 64 ? 64 : (maxc + 255) / 256, n_scenes), 256, 0, st>>>(
+                raw, scene_stride, stride, slots, h->counts[kind].as<int32_t>(), h->slot_points[kind], first_scene);
+            h->launches++;
+            CK(cudaGetLastError());
+        }
+    }
+    cloud_filter_nan_kernel<<<n_scenes, 256, 0, st>>>(slots, h->counts[kind].as<int32_t>(),
+                                                       h->slot_points[kind], first_scene);
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
+
+int ampc_cloud_set(ampc_handle *h, int32_t scene, int32_t kind, const void *xyz_host, int32_t n,
+                   int32_t stride_bytes) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = cloud_set_common(h, kind, scene, 1, xyz_host ? xyz_host : (const void *)h, false, &n, 0,
+                              stride_bytes, h->stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPC_OK;
+}
+int ampc_cloud_set_batch(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
+                         const void *xyz_host, const int32_t *counts, int64_t scene_stride_bytes,
+                         int32_t stride_bytes) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = cloud_set_common(h, kind, first_scene, n_scenes, xyz_host, false, counts,
+                              scene_stride_bytes, stride_bytes, h->stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return AMPC_OK;
+}
+int ampc_cloud_set_batch_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
+                             const void *xyz_dev, const int32_t *counts_host,
+                             int64_t scene_stride_bytes, void *stream) {
+    return cloud_set_common(h, kind, first_scene, n_scenes, xyz_dev, true, counts_host,
+                            scene_stride_bytes, 16, (cudaStream_t)stream);
+}
+int ampc_cloud_count(ampc_handle *h, int32_t scene, int32_t kind, int32_t *n_out) {
+    if (!h || !n_out) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, kind);
+    if (rc) return rc;
+    if (scene < 0 || scene >= h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "scene out of range");
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(n_out, h->counts[kind].as<int32_t>() + scene, 4, cudaMemcpyDeviceToHost));
+    return AMPC_OK;
+}
+
+// ---- k-NN -------------------------------------------------------------------
+int ampc_knn_batch_dev(ampc_handle *h, int32_t kind, int32_t B, const int32_t *scene_of_dev,
+                       const double *queries_dev, int32_t Q, int32_t k, int32_t *idx_dev,
+                       double *dist2_dev, double *pts_dev, int32_t *count_dev, void *stream) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, kind);
+    if (rc) return rc;
+    if (!queries_dev) return fail(h, AMPC_ERR_INVALID, "null queries");
+    if (!scene_of_dev && B > h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "identity scene map needs B <= max_scenes");
+    CK(cudaSetDevice(h->cfg.device));
+    return launch_knn(h, kind, B, scene_of_dev, queries_dev, Q, k, idx_dev, dist2_dev, count_dev,
+                      pts_dev, (int64_t)Q * k * 3, (int64_t)k * 3, (cudaStream_t)stream);
+}
+
+int ampc_knn_batch(ampc_handle *h, int32_t kind, int32_t B, const int32_t *scene_of,
+                   const double *queries, int32_t Q, int32_t k, int32_t *idx_out, double *dist2_out,
+                   double *pts_out, int32_t *count_out) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, kind);
+    if (rc) return rc;
+    if (B < 1 || Q < 1 || k < 1) return fail(h, AMPC_ERR_INVALID, "B, Q, k must be positive");
+    if (!queries) return fail(h, AMPC_ERR_INVALID, "null queries");
+    if (scene_of)
+        for (int b = 0; b < B; ++b)
+            if (scene_of[b] < 0 || scene_of[b] >= h->cfg.max_scenes)
+                return fail(h, AMPC_ERR_CAPACITY, "scene_of entry out of range");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t nq = (size_t)B * Q, nr = nq * k;
+    CK(h->queries.reserve(nq * 3 * 8));
+    CK(h->knn_idx.reserve(nr * 4));
+    CK(h->knn_d2.reserve(nr * 8));
+    CK(h->knn_cnt.reserve(nq * 4));
+    CK(h->scene_of.reserve((size_t)B * 4));
+    if (pts_out) CK(h->knn_pts.reserve(nr * 3 * 8));
+    CK(cudaMemcpyAsync(h->queries.p, queries, nq * 3 * 8, cudaMemcpyHostToDevice, st));
+    if (scene_of) CK(cudaMemcpyAsync(h->scene_of.p, scene_of, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    rc = ampc_knn_batch_dev(h, kind, B, scene_of ? h->scene_of.as<int32_t>() : nullptr,
+                            h->queries.as<double>(), Q, k, h->knn_idx.as<int32_t>(),
+                            h->knn_d2.as<double>(), pts_out ? h->knn_pts.as<double>() : nullptr,
+                            h->knn_cnt.as<int32_t>(), st);
+    if (rc) return rc;
+    if (idx_out) CK(cudaMemcpyAsync(idx_out, h->knn_idx.p, nr * 4, cudaMemcpyDeviceToHost, st));
+    if (dist2_out) CK(cudaMemcpyAsync(dist2_out, h->knn_d2.p, nr * 8, cudaMemcpyDeviceToHost, st));
+    if (pts_out) CK(cudaMemcpyAsync(pts_out, h->knn_pts.p, nr * 3 * 8, cudaMemcpyDeviceToHost, st));
+    if (count_out) CK(cudaMemcpyAsync(count_out, h->knn_cnt.p, nq * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMPC_OK;
+}
+
+// ---- solve ------------------------------------------------------------------
+int ampc_solve_batch_dev(ampc_handle *h, int32_t B, const double *p_prefix_dev, double *w_inout_dev,
+                         ampc_solve_info *info_dev, void *stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!p_prefix_dev || !w_inout_dev) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    SolveOut *info = info_dev ? reinterpret_cast<SolveOut *>(info_dev) : h->info.as<SolveOut>();
+    return launch_solve(h, B, p_prefix_dev, w_inout_dev, info, (cudaStream_t)stream);
+}
+
+int ampc_solve_batch(ampc_handle *h, int32_t B, const double *p_prefix, double *w_inout,
+                     ampc_solve_info *info_out) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!p_prefix || !w_inout) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->prefix.p, p_prefix, (size_t)B * h->n_prefix * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->w.p, w_inout, (size_t)B * h->n_w * 8, cudaMemcpyHostToDevice, st));
+    rc = launch_solve(h, B, h->prefix.as<double>(), h->w.as<double>(), h->info.as<SolveOut>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(w_inout, h->w.p, (size_t)B * h->n_w * 8, cudaMemcpyDeviceToHost, st));
+    if (info_out)
+        CK(cudaMemcpyAsync(info_out, h->info.p, (size_t)B * sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMPC_OK;
+}
+
+// ---- one round: k-NN at the reference waypoints + prefix packing + solve ------
+int ampc_round_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev, const double *x0_dev,
+                         const double *ref_dev, const double *pos_x_dev, double speed,
+                         double safety_distance, double *w_inout_dev, ampc_solve_info *info_dev,
+                         int32_t *need_replan_dev, void *stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    rc = check_kind(h, AMPC_CLOUD_OBSTACLE);
+    if (rc) return rc;
+    if (!x0_dev || !ref_dev || !w_inout_dev) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    if (h->cfg.K < 1) return fail(h, AMPC_ERR_INVALID, "round needs K >= 1");
+    if (!scene_of_dev && B > h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "identity scene map needs B <= max_scenes");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cfg.N, K = h->cfg.K;
+    double *prefix = h->prefix.as<double>();
+    pack_prefix_kernel<<<B, 64, 0, st>>>(B, N, K, x0_dev, ref_dev, pos_x_dev, speed, N * h->cfg.dt,
+                                         prefix, h->n_prefix, h->queries.as<double>());
+    h->launches++;
+    CK(cudaGetLastError());
+    // the k-NN kernel writes the K neighbours of waypoint q straight into the
+    // obstacle block of the prefix: obst_{q,j} at 10 + 10N + 3(Kq + j)
+    rc = launch_knn(h, AMPC_CLOUD_OBSTACLE, B, scene_of_dev, h->queries.as<double>(), N, K,
+                    h->knn_idx.as<int32_t>(), h->knn_d2.as<double>(), h->knn_cnt.as<int32_t>(),
+                    prefix + 10 + 10 * N, h->n_prefix, 3 * K, st);
+    if (rc) return rc;
+    if (need_replan_dev) {
+        replan_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, K, h->knn_d2.as<double>(),
+                                                       h->knn_cnt.as<int32_t>(), safety_distance,
+                                                       need_replan_dev);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    SolveOut *info = info_dev ? reinterpret_cast<SolveOut *>(info_dev) : h->info.as<SolveOut>();
+    return launch_solve(h, B, prefix, w_inout_dev, info, st);
+}
+
+int ampc_round_batch(ampc_handle *h, int32_t B, const int32_t *scene_of, const double *x0,
+                     const double *ref, const double *pos_x, double speed, double safety_distance,
+                     double *w_inout, ampc_solve_info *info_out, int32_t *need_replan_out) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!x0 || !ref || !w_inout) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    if (scene_of)
+        for (int b = 0; b < B; ++b)
+            if (scene_of[b] < 0 || scene_of[b] >= h->cfg.max_scenes)
+                return fail(h, AMPC_ERR_CAPACITY, "scene_of entry out of range");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t N = h->cfg.N;
+    CK(cudaMemcpyAsync(h->x0.p, x0, (size_t)B * 10 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ref.p, ref, (size_t)B * N * 10 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->w.p, w_inout, (size_t)B * h->n_w * 8, cudaMemcpyHostToDevice, st));
+    if (scene_of) CK(cudaMemcpyAsync(h->scene_of.p, scene_of, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    if (pos_x) CK(cudaMemcpyAsync(h->posx.p, pos_x, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    rc = ampc_round_batch_dev(h, B, scene_of ? h->scene_of.as<int32_t>() : nullptr, h->x0.as<double>(),
+                              h->ref.as<double>(), pos_x ? h->posx.as<double>() : nullptr, speed,
+                              safety_distance, h->w.as<double>(),
+                              reinterpret_cast<ampc_solve_info *>(h->info.p),
+                              need_replan_out ? h->replan.as<int32_t>() : nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(w_inout, h->w.p, (size_t)B * h->n_w * 8, cudaMemcpyDeviceToHost, st));
+    if (info_out)
+        CK(cudaMemcpyAsync(info_out, h->info.p, (size_t)B * sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
+    if (need_replan_out)
+        CK(cudaMemcpyAsync(need_replan_out, h->replan.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMPC_OK;
+}
+
+int ampc_last_prefix_dev(ampc_handle *h, const double **p) {
+    if (!h || !p) return AMPC_ERR_INVALID;
+    *p = h->prefix.as<double>();
+    return AMPC_OK;
+}
+
+// ---- best-of-G ----------------------------------------------------------------
+int ampc_best_of_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_info *info_dev,
+                     int32_t *argmin_dev, double *best_cost_dev, void *stream) {
+    if (!h) return AMPC_ERR_INVALID;
+    if (n_scenes < 1 || G < 1 || !info_dev || !argmin_dev || !best_cost_dev)
+        return fail(h, AMPC_ERR_INVALID, "bad best_of arguments");
+    CK(cudaSetDevice(h->cfg.device));
+    best_of_kernel<<<(n_scenes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        n_scenes, G, reinterpret_cast<const SolveOut *>(info_dev), argmin_dev, best_cost_dev);
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
+
+int ampc_best_of(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_info *info,
+                 int32_t *argmin_out, double *best_cost_out) {
+    if (!h) return AMPC_ERR_INVALID;
+    if (n_scenes < 1 || G < 1 || !info || !argmin_out || !best_cost_out)
+        return fail(h, AMPC_ERR_INVALID, "bad best_of arguments");
+    const int64_t B = (int64_t)n_scenes * G;
+    if (B > h->cfg.max_batch) return fail(h, AMPC_ERR_CAPACITY, "n_scenes*G exceeds max_batch");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->info.p, info, (size_t)B * sizeof(SolveOut), cudaMemcpyHostToDevice, st));
+    int rc = ampc_best_of_dev(h, n_scenes, G, reinterpret_cast<const ampc_solve_info *>(h->info.p),
+                              h->bo_arg.as<int32_t>(), h->bo_cost.as<double>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(argmin_out, h->bo_arg.p, (size_t)n_scenes * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(best_cost_out, h->bo_cost.p, (size_t)n_scenes * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMPC_OK;
+}
+
+} // extern "C"

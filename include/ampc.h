@@ -1,0 +1,197 @@
+/* ampc.h — C-ABI of the B200-native Avoid-MPC hot path (libampc.so).
+ *
+ * This is the drop-in boundary: plain C, opaque handle, caller-owned buffers,
+ * int status returns, no exceptions and no torch/CUDA types in any signature
+ * (device pointers and streams travel as void*).  Every entry point names the
+ * reference interface it replaces; paths are relative to
+ * roswrapper/ros/src/avoid_mpc/ of SJTU-ViSYS-team/Avoid-MPC.
+ *
+ * Two flavours of each batch call:
+ *   ampc_xxx      host buffers in / out (copies inside the call, synchronous)
+ *   ampc_xxx_dev  device buffers in / out, asynchronous on `stream`
+ *
+ * Sizes for a handle created with horizon N and K neighbours per stage:
+ *   n_w      = 10 + 14 N                 decision vector [X_0,U_0,...,U_{N-1},X_N]
+ *   n_prefix = 20 + 10 N + 3 K N         vecRefStates = [x0 | ref N*10 | obst N*K*3 | target]
+ * (tools/mpc_obstacle_casadi.py:76-94,158,164,217; src/AvoidanceStateMachine.cpp:236-257)
+ */
+#ifndef AMPC_H
+#define AMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPC_API_VERSION 1
+
+/* status codes returned by every function */
+enum {
+    AMPC_OK = 0,
+    AMPC_ERR_INVALID = 1,  /* bad argument (null, out of range, wrong size) */
+    AMPC_ERR_CUDA = 2,     /* CUDA runtime error or no device: ampc_last_error() has the text */
+    AMPC_ERR_CAPACITY = 3, /* batch / scene / point count exceeds what the handle was created for */
+    AMPC_ERR_UNSUPPORTED = 4
+};
+
+/* per-instance solver status (ampc_solve_* `status_out`); the reference never
+ * inspects IPOPT's return status (src/HighLvlMpc.cpp:116-122) */
+enum {
+    AMPC_SOLVE_CONVERGED = 0,
+    AMPC_SOLVE_MAX_ITER = 1,
+    AMPC_SOLVE_STALLED = 2, /* line search could not make progress */
+    AMPC_SOLVE_NUMERIC = 3  /* NaN / inertia correction exhausted */
+};
+
+/* which per-scene cloud a call refers to (include/FrameKDMap.h:11-13:
+ * Frame::pointCloud and Frame::edgeCloud) */
+enum { AMPC_CLOUD_OBSTACLE = 0, AMPC_CLOUD_EDGE = 1 };
+
+typedef struct ampc_handle ampc_handle;
+
+typedef struct ampc_config {
+    int32_t N;                /* horizon = int(T/dt)            (src/HighLvlMpc.cpp:9)            */
+    int32_t K;                /* nearest_point_num              (config/mpc_parameters.yaml:5)    */
+    double dt;                /* mpc_dt                         (config/mpc_parameters.yaml:2)    */
+    int32_t max_batch;        /* most MPC instances per batch call                                 */
+    int32_t max_scenes;       /* scene slots (one Obstacle + one Edge cloud each)                  */
+    int32_t max_points;       /* capacity of one Obstacle cloud slot, points                       */
+    int32_t max_edge_points;  /* capacity of one Edge cloud slot, points (0: no edge clouds)       */
+    int32_t device;           /* CUDA device ordinal                                               */
+} ampc_config;
+
+/* Interior-point options (role of the ipopt.* dictionary, src/HighLvlMpc.cpp:17-23).
+ * ampc_default_solver_opts() fills the values the parity tests run with. */
+typedef struct ampc_solver_opts {
+    double tol;        /* KKT tolerance                 (ipopt.tol)      default 1e-8 */
+    int32_t max_iter;  /* iteration cap                 (ipopt.max_iter) default 100  */
+    double mu_init;    /* initial barrier parameter                      default 0.1  */
+    double bound_push; /* initial push of U off its bounds               default 1e-2 */
+    double bound_frac; /*                                                default 1e-2 */
+    double eps_min;    /* floor of the |v.n| smoothing, m/s              default 1e-5 */
+    double eps_scale;  /* smoothing eps = max(eps_min, eps_scale*mu)     default 1.0  */
+} ampc_solver_opts;
+
+/* one record per instance written by the solve calls */
+typedef struct ampc_solve_info {
+    double cost;     /* NLP objective f at the returned point (un-smoothed) */
+    double kkt_dual; /* | grad_U L |_inf  (x-stationarity holds exactly via the adjoint) */
+    double kkt_compl;/* max slack*multiplier */
+    double mu;       /* final barrier parameter */
+    int32_t iters;
+    int32_t status;  /* AMPC_SOLVE_* */
+    int32_t n_reg;   /* iterations that needed inertia-correcting regularisation */
+    int32_t n_backtrack;
+} ampc_solve_info;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* replaces ObstacleAvoidanceMPC::ObstacleAvoidanceMPC(T, dt, soPath)  (src/HighLvlMpc.cpp:5-59)
+ * and the FrameKDMap constructor; N and K were baked into the codegen .so there. */
+int ampc_create(const ampc_config *cfg, ampc_handle **out);
+void ampc_destroy(ampc_handle *h);
+/* text of the last error on this handle (or of the last failed ampc_create when h == NULL) */
+const char *ampc_last_error(const ampc_handle *h);
+int ampc_api_version(void);
+
+/* ---- parameters (src/HighLvlMpc.cpp:60-92) ------------------------------ */
+int ampc_set_weights(ampc_handle *h, const double weights[25]);     /* SetupWeights        */
+int ampc_set_tau(ampc_handle *h, const double tau[4]);              /* SetupTau            */
+int ampc_set_gains(ampc_handle *h, const double gains[4]);          /* SetupGains (unused by the default dynamics, tools/mpc_obstacle_casadi.py:114-121) */
+int ampc_set_radius(ampc_handle *h, double drone_radius);           /* SetDroneRadius      */
+int ampc_set_accel_limits(ampc_handle *h, double a_min_z, double a_max_z, double a_max_xy,
+                          double a_max_yaw_dot);                    /* SetDroneAccelLimits */
+void ampc_default_solver_opts(ampc_solver_opts *o);
+int ampc_set_solver_opts(ampc_handle *h, const ampc_solver_opts *o);
+/* discrete dynamics X+ = Phi X + Gam U + gam the solver uses (RK4 x 4 of the
+ * affine ODE, tools/mpc_obstacle_casadi.py:106-122,338-357); row-major. */
+int ampc_get_dynamics(ampc_handle *h, double Phi[100], double Gam[40], double gam[10]);
+
+/* ---- clouds: replaces KDTreeTwo::InitializeNew (include/kd_tree_two.h:75-106)
+ * as called by FrameKDMap::AddVertex (src/FrameKDMap.cpp:44-47).  Points whose
+ * x is NaN are dropped and the rest keep their order (kd_tree_two.h:99-101), so
+ * neighbour indices refer to the filtered cloud exactly as in the reference.
+ * xyz: records of `stride_bytes` (>= 12) starting with float x,y,z
+ * (pcl::PointXYZ: stride 16). */
+int ampc_cloud_set(ampc_handle *h, int32_t scene, int32_t kind, const void *xyz_host, int32_t n,
+                   int32_t stride_bytes);
+/* n_scenes clouds, scene s at xyz_host + s*scene_stride_bytes holding counts[s] points */
+int ampc_cloud_set_batch(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
+                         const void *xyz_host, const int32_t *counts, int64_t scene_stride_bytes,
+                         int32_t stride_bytes);
+/* same, source already in device memory (16-byte records only); async on stream */
+int ampc_cloud_set_batch_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
+                             const void *xyz_dev, const int32_t *counts_host,
+                             int64_t scene_stride_bytes, void *stream);
+/* number of points held for (scene, kind) after the NaN filter (synchronises) */
+int ampc_cloud_count(ampc_handle *h, int32_t scene, int32_t kind, int32_t *n_out);
+
+/* ---- k-NN: replaces KDTreeTwo::SearchForNearest (include/kd_tree_two.h:108-133)
+ * behind FrameKDMap::QueryNearest's current-frame path (src/FrameKDMap.cpp:254-275,
+ * 339-345) for B instances x Q queries at once.
+ *   scene_of[B]  scene slot of each instance (NULL: instance b uses scene b)
+ *   queries      B*Q*3 doubles
+ *   idx_out      B*Q*k int32, ascending (dist2, index); -1 beyond count
+ *   dist2_out    B*Q*k doubles (SQUARED distances, as the reference); +inf beyond count
+ *   pts_out      B*Q*k*3 doubles, neighbour coordinates widened from float; (1e4,1e4,1e4)
+ *                beyond count (src/AvoidanceStateMachine.cpp:223-226).  May be NULL.
+ *   count_out    B*Q int32: results per query = min(k, n) except 0 when n == k
+ *                (the reference's quirk, kd_tree_two.h:117-124)
+ * Exact: dist2 = ((dx*dx + dy*dy) + dz*dz) in double from float coordinates, each
+ * operation rounded separately (include/nanoflann_two.hpp:590-599). k <= 32. */
+int ampc_knn_batch(ampc_handle *h, int32_t kind, int32_t B, const int32_t *scene_of,
+                   const double *queries, int32_t Q, int32_t k, int32_t *idx_out,
+                   double *dist2_out, double *pts_out, int32_t *count_out);
+int ampc_knn_batch_dev(ampc_handle *h, int32_t kind, int32_t B, const int32_t *scene_of_dev,
+                       const double *queries_dev, int32_t Q, int32_t k, int32_t *idx_dev,
+                       double *dist2_dev, double *pts_dev, int32_t *count_dev, void *stream);
+
+/* ---- solve: replaces ObstacleAvoidanceMPC::Solve (src/HighLvlMpc.cpp:93-137)
+ * for B instances.  p_prefix: B*n_prefix doubles (vecRefStates; the gains/tau/
+ * weights/radius tail is appended from the handle as Solve does, :97-108).
+ * w_inout: B*n_w doubles, warm start in (mNlpW0 role, :110,129; only its U part
+ * is used, X is rolled out from x0), solution out.  u = w[10:14],
+ * x0Array[i] = w[14i:14i+14] (:122-136).  info_out may be NULL. */
+int ampc_solve_batch(ampc_handle *h, int32_t B, const double *p_prefix, double *w_inout,
+                     ampc_solve_info *info_out);
+int ampc_solve_batch_dev(ampc_handle *h, int32_t B, const double *p_prefix_dev, double *w_inout_dev,
+                         ampc_solve_info *info_dev, void *stream);
+
+/* ---- one round of the control tick for B instances: ProcessWaypoints +
+ * GetRefStates + Solve (src/AvoidanceStateMachine.cpp:204-257,337) = Q=N k-NN
+ * queries at the reference-path positions on the Obstacle cloud, prefix packing
+ * with the target rule (:250-255) and the NLP solve.
+ *   x0[B*10], ref[B*N*10], scene_of[B] (NULL: identity), pos_x[B] (mPos.x of the
+ *   target rule; NULL: x0[0]), speed (mSpeed).
+ *   need_replan_out[B] (may be NULL): nearest obstacle <= safety_distance or no
+ *   neighbour at some waypoint (:228-231). */
+int ampc_round_batch(ampc_handle *h, int32_t B, const int32_t *scene_of, const double *x0,
+                     const double *ref, const double *pos_x, double speed, double safety_distance,
+                     double *w_inout, ampc_solve_info *info_out, int32_t *need_replan_out);
+int ampc_round_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev,
+                         const double *x0_dev, const double *ref_dev, const double *pos_x_dev,
+                         double speed, double safety_distance, double *w_inout_dev,
+                         ampc_solve_info *info_dev, int32_t *need_replan_dev, void *stream);
+/* device address of the packed prefixes of the last round (B*n_prefix doubles) */
+int ampc_last_prefix_dev(ampc_handle *h, const double **p_prefix_dev);
+
+/* ---- best-of-G reduction over the G initial guesses of each scene (Edge-tree
+ * guesses, src/AvoidanceStateMachine.cpp:259-281 generalised): instances are laid
+ * out scene-major (b = s*G + g).  argmin_out[s] = g of the lowest cost among
+ * instances whose status is CONVERGED or MAX_ITER (ties: lowest g); -1 if none. */
+int ampc_best_of(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_info *info,
+                 int32_t *argmin_out, double *best_cost_out);
+int ampc_best_of_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_info *info_dev,
+                     int32_t *argmin_dev, double *best_cost_dev, void *stream);
+
+/* ---- instrumentation ---------------------------------------------------- */
+/* kernels launched by this handle since creation (for bench.py's gpu_launches) */
+int64_t ampc_launch_count(const ampc_handle *h);
+/* the handle's own stream (void* cudaStream_t) used by the host-buffer calls */
+void *ampc_stream(ampc_handle *h);
+int ampc_synchronize(ampc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPC_H */

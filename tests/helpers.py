@@ -1,0 +1,35 @@
+"""Shared builders for the parity tests (seeded inputs of SURVEY.md §8d)."""
+import numpy as np
+
+import avoid_mpc_b200 as A
+from oracle import oracle as O
+
+D, S = A.defaults, A.synth
+
+
+def make_instances(scene_ids, N, K, npts, cloud_fn=None):
+    """Returns dict with clouds (list of [n,4] f32), x0 [B,10], ref [B,N,10], tgt [B,10],
+    obstacle blocks from the ORACLE k-NN [B,N,K,3], prefixes [B,n_prefix], full params."""
+    clouds, x0s, refs, tgts, obsts, prefixes, params = [], [], [], [], [], [], []
+    for sid in scene_ids:
+        c = cloud_fn(sid) if cloud_fn else S.forest_cloud(sid, npts)[0]
+        x0, ref, tgt = S.states(sid, N, 1.0 / N if N != 20 else D.BENCH_DT)
+        idx, d2, cnt = O.knn_bruteforce(c, ref[:, :3], K)
+        ob = np.full((N, K, 3), 1e4)
+        cf = O.filter_nan(c)
+        for q in range(N):
+            ob[q, :cnt[q]] = cf[idx[q, :cnt[q]], :3].astype(np.float64)
+        pre = S.pack_prefix(x0, ref, ob, tgt)
+        clouds.append(c), x0s.append(x0), refs.append(ref), tgts.append(tgt), obsts.append(ob)
+        prefixes.append(pre), params.append(S.full_params(pre))
+    return dict(clouds=clouds, x0=np.stack(x0s), ref=np.stack(refs), tgt=np.stack(tgts),
+                obst=np.stack(obsts), prefix=np.stack(prefixes), params=np.stack(params))
+
+
+def oracle_solve_batch(N, K, dt, params, W0, **opts):
+    lb, ub = D.u_bounds()
+    W, infos = O.solve_batch(N, K, dt, params, W0, lb, ub, O.default_opts(**opts))
+    st = np.array([i.status for i in infos])
+    it = np.array([i.iters for i in infos])
+    cost = np.array([i.cost for i in infos])
+    return W, st, it, cost

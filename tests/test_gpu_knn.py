@@ -1,0 +1,115 @@
+"""GPU parity: exact k-NN through the C-ABI vs the CPU oracle (bit-exact indices and dist2)."""
+import numpy as np
+import pytest
+
+import avoid_mpc_b200 as A
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+S = A.synth
+
+
+def _check(h, clouds, queries, k, scene_of=None):
+    idx, d2, pts, cnt = h.knn(queries, k, scene_of=scene_of)
+    B, Q = queries.shape[:2]
+    for b in range(B):
+        c = clouds[b if scene_of is None else scene_of[b]]
+        cf = O.filter_nan(c)
+        ri, rd, rc = O.knn_bruteforce(cf, queries[b], k)
+        assert (cnt[b] == rc).all()
+        assert (idx[b] == ri).all(), f"index mismatch instance {b}"
+        assert (d2[b] == rd).all(), "dist2 must be bit-exact"
+        for q in range(Q):
+            m = rc[q]
+            assert (pts[b, q, :m] == cf[ri[q, :m], :3].astype(np.float64)).all()
+            assert (pts[b, q, m:] == 1e4).all()
+
+
+@pytest.mark.parametrize("npts,k", [(10000, 8), (50000, 16), (3072, 3), (10000, 1), (2000, 32)])
+def test_knn_forest_matches_oracle(npts, k):
+    B, Q = 6, 20
+    h = A.Handle(N=Q, K=min(k, 32), max_batch=B, max_points=npts)
+    clouds = [S.forest_cloud(100 + s, npts)[0] for s in range(B)]
+    for s, c in enumerate(clouds):
+        h.cloud_set(s, c)
+    queries = np.stack([S.states(100 + s, Q)[1][:, :3] for s in range(B)])
+    _check(h, clouds, queries, k)
+    h.close()
+
+
+def test_knn_matches_reference_tree_when_tie_free(oracle):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    B, Q, k, npts = 4, 20, 16, 20000
+    h = A.Handle(N=Q, K=k, max_batch=B, max_points=npts)
+    for s in range(B):
+        c = S.random_cloud(7 + s, npts)
+        h.cloud_set(s, c)
+        q = np.random.default_rng(s).uniform([0, -3, 0.5], [20, 3, 3], (Q, 3))
+        assert O.is_tie_free(c, q, k)
+        idx, d2, _, cnt = h.knn(q[None], k, scene_of=np.array([s], dtype=np.int32))
+        ri, rd, rc = O.RefTree(c).search(q, k)
+        assert (idx[0] == ri).all() and (d2[0] == rd).all() and (cnt[0] == rc).all()
+    h.close()
+
+
+def test_knn_edge_cases():
+    Q, k = 5, 4
+    h = A.Handle(N=Q, K=k, max_batch=8, max_points=4096)
+    rng = np.random.default_rng(0)
+    q = rng.uniform(-1, 1, (1, Q, 3))
+    # empty cloud -> no results (kd_tree_two.h:112)
+    h.cloud_set(0, np.zeros((0, 4), dtype=np.float32))
+    idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([0], dtype=np.int32))
+    assert (cnt == 0).all() and (idx == -1).all() and np.isinf(d2).all() and (pts == 1e4).all()
+    # fewer points than k -> n results; exactly k points -> 0 results (kd_tree_two.h:117-124)
+    for s, n in ((1, 3), (2, 4), (3, 5)):
+        c = S.random_cloud(s, n, lo=(-1, -1, -1), hi=(1, 1, 1))
+        h.cloud_set(s, c)
+        idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([s], dtype=np.int32))
+        ri, rd, rc = O.knn_bruteforce(c, q[0], k)
+        assert (cnt[0] == rc).all() and (idx[0] == ri).all() and (d2[0] == rd).all()
+        assert (cnt[0] == (n if n < k else (k if n > k else 0))).all()
+    # NaN x dropped and the rest re-indexed (kd_tree_two.h:99-101); ragged size; stride 12
+    c = S.random_cloud(9, 1237, lo=(-1, -1, -1), hi=(1, 1, 1))
+    c[::7, 0] = np.nan
+    c[5, 1] = np.nan  # NaN y stays in the cloud but can never be a neighbour
+    h.cloud_set(4, c)
+    assert h.cloud_count(4) == int((~np.isnan(c[:, 0])).sum())
+    idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([4], dtype=np.int32))
+    ri, rd, rc = O.knn_bruteforce(O.filter_nan(c), q[0], k)
+    assert (idx[0] == ri).all() and (d2[0] == rd).all()
+    c3 = np.ascontiguousarray(S.random_cloud(11, 999)[:, :3])
+    h.cloud_set(5, c3)
+    qq = rng.uniform([0, -3, 0], [20, 3, 3], (1, Q, 3))
+    idx, d2, pts, cnt = h.knn(qq, k, scene_of=np.array([5], dtype=np.int32))
+    ri, rd, rc = O.knn_bruteforce(c3, qq[0], k)
+    assert (idx[0] == ri).all() and (d2[0] == rd).all()
+    h.close()
+
+
+def test_knn_duplicate_points_canonical_order():
+    """Exact ties are returned in (dist2, index) order."""
+    c = np.ones((64, 4), dtype=np.float32)
+    c[:, :3] = np.array([1.0, 2.0, 3.0], dtype=np.float32)
+    c[40:, 0] = 5.0
+    h = A.Handle(N=1, K=8, max_batch=1, max_points=64)
+    h.cloud_set(0, c)
+    idx, d2, _, cnt = h.knn(np.zeros((1, 1, 3)), 8)
+    assert (idx[0, 0] == np.arange(8)).all() and cnt[0, 0] == 8
+    h.close()
+
+
+def test_knn_single_instance_uses_segments_and_large_cloud():
+    """B = 1 spreads one cloud over many CTAs (multi-segment merge path); 1M points."""
+    npts, Q, k = 1000000, 20, 16
+    h = A.Handle(N=Q, K=k, max_batch=1, max_points=npts)
+    c = S.random_cloud(3, npts, lo=(0, -20, 0), hi=(40, 20, 10))
+    h.cloud_set(0, c)
+    q = np.random.default_rng(1).uniform([0, -5, 0.5], [30, 5, 3], (1, Q, 3))
+    idx, d2, _, cnt = h.knn(q, k)
+    ri, rd, rc = O.knn_bruteforce(c, q[0], k)
+    assert (idx[0] == ri).all() and (d2[0] == rd).all()
+    # size-independent property: results are sorted and are true distances of the indices
+    assert (np.diff(d2[0], axis=1) >= 0).all()
+    h.close()

@@ -1,0 +1,75 @@
+"""GPU parity: the batched interior-point solve through the C-ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import avoid_mpc_b200 as A
+from oracle import oracle as O
+from helpers import make_instances, oracle_solve_batch
+
+pytestmark = pytest.mark.gpu
+D, S = A.defaults, A.synth
+
+TRAJ_TOL = 1e-4   # north-star tolerance on state/control trajectories (l_inf)
+TIGHT_TOL = 1e-6  # what the two implementations actually agree to at convergence
+
+
+def test_dynamics_match_oracle():
+    h = A.Handle(N=20, K=16, max_batch=1, max_points=16)
+    Phi, Gam, gam = h.dynamics()
+    oP, oG, og = O.dyn_matrices(D.TAU, 0.05)
+    assert np.abs(Phi - oP).max() < 1e-15 and np.abs(Gam - oG).max() < 1e-15 and np.abs(gam - og).max() < 1e-15
+    h.close()
+
+
+@pytest.mark.parametrize("N,K,npts,kind", [(20, 16, 10000, "cold"), (20, 16, 10000, "ref"),
+                                           (20, 8, 10000, "ref"), (30, 3, 3072, "cold")])
+def test_solve_matches_oracle(N, K, npts, kind):
+    B = 48
+    dt = 1.0 / N if N != 20 else 0.05
+    inst = make_instances(range(200, 200 + B), N, K, npts)
+    W0 = np.stack([S.warm_start(kind, inst["x0"][b], inst["ref"][b], N) for b in range(B)])
+    h = A.Handle(N=N, K=K, dt=dt, max_batch=B, max_points=16)
+    W, info = h.solve(inst["prefix"], W0)
+    oW, ost, oit, ocost = oracle_solve_batch(N, K, dt, inst["params"], W0)
+    both = (info["status"] == 0) & (ost == 0)
+    assert both.mean() >= 0.9, f"converged on both sides: {both.mean():.2f}"
+    err = np.abs(W - oW).max(axis=1)
+    same = err[both] < TRAJ_TOL
+    # identical algorithm: every instance converged on both sides lands on the same optimum
+    assert same.mean() >= 0.98, f"same optimum fraction {same.mean():.3f}, worst {err[both].max():.2e}"
+    assert np.median(err[both]) < TIGHT_TOL
+    rel = np.abs(info["cost"][both] - ocost[both]) / np.maximum(1.0, np.abs(ocost[both]))
+    assert np.median(rel) < 1e-9
+    # KKT residuals reported by the kernel
+    assert (info["kkt_dual"][info["status"] == 0] <= 1e-8).all()
+    assert (info["kkt_compl"][info["status"] == 0] <= 1e-8).all()
+    h.close()
+
+
+def test_solution_is_feasible_and_outputs_slice_like_reference():
+    N, K, B = 20, 16, 16
+    inst = make_instances(range(300, 300 + B), N, K, 10000)
+    W0 = np.stack([S.warm_start("ref", inst["x0"][b], inst["ref"][b], N) for b in range(B)])
+    h = A.Handle(N=N, K=K, max_batch=B, max_points=16)
+    W, info = h.solve(inst["prefix"], W0)
+    lb, ub = D.u_bounds()
+    for b in range(B):
+        g = O.g(N, K, W[b], inst["params"][b], 0.05)
+        assert np.abs(g).max() < 1e-9            # X_0 = x0 and the dynamics hold
+        U = np.stack([W[b][14 * k + 10:14 * k + 14] for k in range(N)])
+        assert (U >= lb - 1e-12).all() and (U <= ub + 1e-12).all()
+        assert abs(O.f(N, K, W[b], inst["params"][b]) - info["cost"][b]) <= 1e-9 * max(1, abs(info["cost"][b]))
+    h.close()
+
+
+def test_status_reports_iteration_cap():
+    N, K, B = 20, 16, 8
+    inst = make_instances(range(400, 400 + B), N, K, 10000)
+    W0 = np.zeros((B, 10 + 14 * N))
+    h = A.Handle(N=N, K=K, max_batch=B, max_points=16)
+    h.set_solver_opts(max_iter=2)
+    W, info = h.solve(inst["prefix"], W0)
+    assert (info["status"] == A.capi.SOLVE_MAX_ITER).all() and (info["iters"] == 2).all()
+    oW, ost, oit, _ = oracle_solve_batch(N, K, 0.05, inst["params"], W0, max_iter=2)
+    assert np.abs(W - oW).max() < 1e-8  # same two iterates
+    h.close()
