@@ -23,10 +23,11 @@ SYMBOLS = [
     "ampc_api_version", "ampc_create", "ampc_destroy", "ampc_last_error",
     "ampc_set_weights", "ampc_set_tau", "ampc_set_gains", "ampc_set_radius", "ampc_set_accel_limits",
     "ampc_default_solver_opts", "ampc_set_solver_opts", "ampc_get_dynamics",
-    "ampc_cloud_set", "ampc_cloud_set_batch", "ampc_cloud_set_batch_dev", "ampc_cloud_count",
+    "ampc_cloud_set", "ampc_cloud_set_batch", "ampc_cloud_set_batch_dev", "ampc_cloud_index_dev", "ampc_cloud_count",
     "ampc_knn_batch", "ampc_knn_batch_dev", "ampc_solve_batch", "ampc_solve_batch_dev",
     "ampc_round_batch", "ampc_round_batch_dev", "ampc_last_prefix_dev",
     "ampc_best_of", "ampc_best_of_dev", "ampc_launch_count", "ampc_stream", "ampc_synchronize",
+    "ampc_profile_enable", "ampc_profile_get",
 ]
 
 
@@ -105,6 +106,9 @@ def lib():
         L.ampc_stream.restype = _vp
         L.ampc_stream.argtypes = [_vp]
         L.ampc_synchronize.argtypes = [_vp]
+        L.ampc_profile_enable.argtypes = [_vp, C.c_int]
+        L.ampc_profile_get.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.ampc_cloud_index_dev.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]
         _lib = L
     return _lib
 
@@ -298,6 +302,18 @@ class Handle:
 
     def best_of_dev(self, n_scenes, G, info_dev, argmin_dev, best_dev, stream=None):
         self._ck(self.L.ampc_best_of_dev(self.h, n_scenes, G, _ptr(info_dev), _ptr(argmin_dev), _ptr(best_dev), stream))
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.ampc_profile_enable(self.h, 1 if on else 0))
+
+    def profile_get(self):
+        """{'index'|'knn'|'solve': (ms total, launches)}"""
+        ms, n = (C.c_double * 3)(), (C.c_int64 * 3)()
+        self._ck(self.L.ampc_profile_get(self.h, ms, n))
+        return {name: (ms[i], n[i]) for i, name in enumerate(("index", "knn", "solve"))}
+
+    def cloud_index_dev(self, first_scene, n_scenes, kind=CLOUD_OBSTACLE, stream=None):
+        self._ck(self.L.ampc_cloud_index_dev(self.h, kind, first_scene, n_scenes, stream))
 
     def launch_count(self):
         return self.L.ampc_launch_count(self.h)

@@ -5,7 +5,7 @@
 
 #include "common.cuh"
 #include "ipm_solve.cuh"
-#include "knn_scan.cuh"
+#include "knn_tiles.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -59,8 +59,9 @@ struct ampc_handle {
     int n_w = 0, n_prefix = 0;
     cudaStream_t stream = nullptr;
     // clouds: [kind] slot buffers + counts
-    DevBuf cloud[2], counts[2];
+    DevBuf cloud[2], counts[2], boxes[2];
     int slot_points[2] = {0, 0};
+    int slot_tiles[2] = {0, 0};
     DevBuf raw_stage; // staging for stride != 16 uploads
     // batch workspaces
     DevBuf queries, prefix, w, info, knn_idx, knn_d2, knn_cnt, knn_pts, scene_of, x0, ref, posx, replan;
@@ -70,6 +71,13 @@ struct ampc_handle {
     std::string err;
     int solve_smem_set = 0;
     int knn_smem_set = 0;
+    // optional per-kernel timing of ampc_round_batch_dev (CUDA events on the caller's stream)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev; // pairs (start, stop), tagged with a section
+    std::vector<int> prof_sec;
+    int prof_pending = 0;
+    double prof_ms[3] = {0, 0, 0};   // index build, k-NN search, solve
+    int64_t prof_n[3] = {0, 0, 0};
 };
 
 namespace {
@@ -233,6 +241,38 @@ __global__ void best_of_kernel(int n_scenes, int G, const SolveOut *info, int32_
     best[s] = c;
 }
 
+constexpr int PROF_RING = 192;
+enum { SEC_INDEX = 0, SEC_KNN = 1, SEC_SOLVE = 2 };
+int prof_drain(ampc_handle *h) {
+    for (int i = 0; i < h->prof_pending; ++i) {
+        float a = 0;
+        CK(cudaEventSynchronize(h->prof_ev[2 * i + 1]));
+        CK(cudaEventElapsedTime(&a, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]));
+        h->prof_ms[h->prof_sec[i]] += a;
+        h->prof_n[h->prof_sec[i]]++;
+    }
+    h->prof_pending = 0;
+    return AMPC_OK;
+}
+// returns the slot to close with prof_end, or -1 when profiling is off
+int prof_begin(ampc_handle *h, int sec, cudaStream_t st, int *slot) {
+    *slot = -1;
+    if (!h->prof) return AMPC_OK;
+    if (h->prof_pending == PROF_RING) {
+        int rc = prof_drain(h);
+        if (rc) return rc;
+    }
+    *slot = h->prof_pending++;
+    h->prof_sec[*slot] = sec;
+    CK(cudaEventRecord(h->prof_ev[2 * *slot], st));
+    return AMPC_OK;
+}
+int prof_end(ampc_handle *h, int slot, cudaStream_t st) {
+    if (slot < 0) return AMPC_OK;
+    CK(cudaEventRecord(h->prof_ev[2 * slot + 1], st));
+    return AMPC_OK;
+}
+
 int check_kind(ampc_handle *h, int kind) {
     if (kind != AMPC_CLOUD_OBSTACLE && kind != AMPC_CLOUD_EDGE)
         return fail(h, AMPC_ERR_INVALID, "kind must be AMPC_CLOUD_OBSTACLE or AMPC_CLOUD_EDGE");
@@ -248,28 +288,23 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
         return fail(h, AMPC_ERR_UNSUPPORTED, "k must be in 1..32");
     if (Q < 1 || B < 1)
         return fail(h, AMPC_ERR_INVALID, "B and Q must be positive");
-    const size_t smem = knn_smem_bytes(Q, k);
-    if (smem > 200 * 1024)
-        return fail(h, AMPC_ERR_UNSUPPORTED, "Q*k too large for the shared-memory top-k lists");
-    if ((int)smem > h->knn_smem_set) {
-        CK(cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->knn_smem_set = (int)smem;
-    }
-    // segments: enough CTAs to fill 148 SMs when the batch is small
+    // one warp per (instance, query); small batches split each cloud's tiles over `segs` warps
     int segs = 1;
-    const int target_ctas = 148 * 4;
-    if (B < target_ctas) {
-        const int max_useful = (h->slot_points[kind] + KNN_WARPS * KNN_TILE * 4 - 1) / (KNN_WARPS * KNN_TILE * 4);
-        segs = (target_ctas + B - 1) / B;
-        if (segs > max_useful)
-            segs = max_useful;
-        if (segs < 1)
-            segs = 1;
+    const int64_t warps = (int64_t)B * Q;
+    const int target_warps = 148 * 16;
+    if (warps < target_warps) {
+        const int max_useful = (h->slot_tiles[kind] + 63) / 64; // >= 64 tiles per segment
+        segs = (int)((target_warps + warps - 1) / warps);
+        if (segs > max_useful) segs = max_useful;
+        if (segs > 64) segs = 64;
+        if (segs < 1) segs = 1;
     }
     KnnParams P{};
     P.clouds = h->cloud[kind].as<float4>();
+    P.boxes = h->boxes[kind].as<float4>();
     P.counts = h->counts[kind].as<int32_t>();
     P.slot_points = h->slot_points[kind];
+    P.slot_tiles = h->slot_tiles[kind];
     P.scene_of = scene_of_dev;
     P.queries = q_dev;
     P.Q = Q;
@@ -282,21 +317,34 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     P.pts_inst_stride = pts_is;
     P.pts_query_stride = pts_qs;
     if (segs > 1) {
-        const size_t n = (size_t)B * segs * Q * k;
+        const size_t n = (size_t)B * Q * segs * k;
         CK(h->ws_d.reserve(n * 8));
         CK(h->ws_i.reserve(n * 4));
-        if (h->ws_counter.bytes < (size_t)B * 4) {
-            CK(h->ws_counter.reserve((size_t)B * 4));
-            CK(cudaMemsetAsync(h->ws_counter.p, 0, h->ws_counter.bytes, st));
-        }
         P.ws_d = h->ws_d.as<double>();
         P.ws_i = h->ws_i.as<uint32_t>();
-        P.ws_counter = h->ws_counter.as<unsigned int>();
     }
-    knn_scan_kernel<<<dim3(segs, B), KNN_THREADS, smem, st>>>(P);
+    const dim3 grid((Q + KS_WARPS - 1) / KS_WARPS, B, segs);
+    knn_search_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
     h->launches++;
     CK(cudaGetLastError());
+    if (segs > 1) {
+        knn_merge_kernel<<<dim3(grid.x, B), KS_WARPS * 32, 0, st>>>(P);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     return AMPC_OK;
+}
+
+int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaStream_t st) {
+    int slot;
+    int rc = prof_begin(h, SEC_INDEX, st, &slot);
+    if (rc) return rc;
+    cloud_index_kernel<<<n_scenes, KI_THREADS, 0, st>>>(h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(),
+                                                        h->counts[kind].as<int32_t>(), h->slot_points[kind],
+                                                        h->slot_tiles[kind], first_scene);
+    h->launches++;
+    CK(cudaGetLastError());
+    return prof_end(h, slot, st);
 }
 
 constexpr int SOLVE_WARPS = 2;
@@ -409,6 +457,9 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
             return bail(e, "cudaMalloc(clouds)");
         if ((e = h->counts[kind].reserve((size_t)cfg->max_scenes * 4)) != cudaSuccess)
             return bail(e, "cudaMalloc(counts)");
+        h->slot_tiles[kind] = (h->slot_points[kind] + KT_TILE - 1) / KT_TILE;
+        if ((e = h->boxes[kind].reserve((size_t)cfg->max_scenes * h->slot_tiles[kind] * 32)) != cudaSuccess)
+            return bail(e, "cudaMalloc(tile boxes)");
         if ((e = cudaMemset(h->counts[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
             return bail(e, "cudaMemset(counts)");
     }
@@ -432,12 +483,13 @@ void ampc_destroy(ampc_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->raw_stage,
+    DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
                      &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost};
     for (DevBuf *b : all)
         b->release();
+    for (auto &e : h->prof_ev) cudaEventDestroy(e);
     if (h->stream)
         cudaStreamDestroy(h->stream);
     delete h;
@@ -557,11 +609,7 @@ static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_sce
             CK(cudaGetLastError());
         }
     }
-    cloud_filter_nan_kernel<<<n_scenes, 256, 0, st>>>(slots, h->counts[kind].as<int32_t>(),
-                                                       h->slot_points[kind], first_scene);
-    h->launches++;
-    CK(cudaGetLastError());
-    return AMPC_OK;
+    return launch_index(h, kind, first_scene, n_scenes, st);
 }
 
 int ampc_cloud_set(ampc_handle *h, int32_t scene, int32_t kind, const void *xyz_host, int32_t n,
@@ -704,10 +752,13 @@ int ampc_round_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev,
     CK(cudaGetLastError());
     // the k-NN kernel writes the K neighbours of waypoint q straight into the
     // obstacle block of the prefix: obst_{q,j} at 10 + 10N + 3(Kq + j)
+    int slot;
+    if ((rc = prof_begin(h, SEC_KNN, st, &slot))) return rc;
     rc = launch_knn(h, AMPC_CLOUD_OBSTACLE, B, scene_of_dev, h->queries.as<double>(), N, K,
                     h->knn_idx.as<int32_t>(), h->knn_d2.as<double>(), h->knn_cnt.as<int32_t>(),
                     prefix + 10 + 10 * N, h->n_prefix, 3 * K, st);
     if (rc) return rc;
+    if ((rc = prof_end(h, slot, st))) return rc;
     if (need_replan_dev) {
         replan_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, K, h->knn_d2.as<double>(),
                                                        h->knn_cnt.as<int32_t>(), safety_distance,
@@ -716,7 +767,50 @@ int ampc_round_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev,
         CK(cudaGetLastError());
     }
     SolveOut *info = info_dev ? reinterpret_cast<SolveOut *>(info_dev) : h->info.as<SolveOut>();
-    return launch_solve(h, B, prefix, w_inout_dev, info, st);
+    if ((rc = prof_begin(h, SEC_SOLVE, st, &slot))) return rc;
+    rc = launch_solve(h, B, prefix, w_inout_dev, info, st);
+    if (rc) return rc;
+    return prof_end(h, slot, st);
+}
+
+int ampc_cloud_index_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes, void *stream) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, kind);
+    if (rc) return rc;
+    if (n_scenes < 1 || first_scene < 0 || first_scene + n_scenes > h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "scene range exceeds ampc_config.max_scenes");
+    CK(cudaSetDevice(h->cfg.device));
+    return launch_index(h, kind, first_scene, n_scenes, (cudaStream_t)stream);
+}
+
+int ampc_profile_enable(ampc_handle *h, int on) {
+    if (!h) return AMPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    if (on && h->prof_ev.empty()) {
+        h->prof_ev.resize(2 * PROF_RING);
+        h->prof_sec.resize(PROF_RING);
+        for (auto &e : h->prof_ev) CK(cudaEventCreate(&e));
+    }
+    int rc = prof_drain(h);
+    if (rc) return rc;
+    h->prof = on != 0;
+    for (int i = 0; i < 3; ++i) {
+        h->prof_ms[i] = 0;
+        h->prof_n[i] = 0;
+    }
+    return AMPC_OK;
+}
+
+int ampc_profile_get(ampc_handle *h, double ms_total[3], int64_t launches[3]) {
+    if (!h) return AMPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    int rc = prof_drain(h);
+    if (rc) return rc;
+    for (int i = 0; i < 3; ++i) {
+        if (ms_total) ms_total[i] = h->prof_ms[i];
+        if (launches) launches[i] = h->prof_n[i];
+    }
+    return AMPC_OK;
 }
 
 int ampc_round_batch(ampc_handle *h, int32_t B, const int32_t *scene_of, const double *x0,

@@ -1,0 +1,429 @@
+// Exact batched k-NN over a flat tile-AABB index (sm_100a).
+//
+// Replaces KDTreeTwo::Initialize + SearchForNearest, i.e. nanoflann buildIndex /
+// findNeighbors / searchLevel (include/kd_tree_two.h:88-133,
+// include/nanoflann_two.hpp:1518-1541,1563-1586,1729-1793), for B instances x Q
+// queries per launch.
+//
+// Index ("build", once per cloud = once per depth frame, src/FrameKDMap.cpp:34-52):
+//   ONE coalesced streaming pass over the 16-byte point records drops the points
+//   whose x is NaN (order preserving, kd_tree_two.h:99-101) and emits the bounding
+//   box of every run of 64 consecutive points (32 B per tile, 3% of the cloud).
+//   Depth-image clouds are stored in raster order, so a run of 64 points is a short
+//   piece of one image row: a thin, tight box.  This pass is the HBM-bound kernel
+//   of the k-NN stage; nothing is sorted and no hierarchy is built.
+// Search: one warp per (instance, query).  Lanes evaluate the exact lower bound of
+//   the query to 32 tile boxes at a time; the nearest tile is scanned first to get a
+//   finite k-th-best bound, then only tiles whose lower bound does not exceed the
+//   current bound are read.  The top-k list lives in registers (lane j = entry j).
+//
+// Arithmetic is the reference's, operation for operation: dist2 = ((dx*dx + dy*dy)
+// + dz*dz) in double from float coordinates, each operation rounded separately
+// (nanoflann_two.hpp:590-599, kd_tree_two.h:34-41); box lower bounds use the same
+// operations in the same order, so rounding can never prune a true neighbour.
+// Indices AND squared distances are bit-exact; order is canonical (dist2, index).
+#pragma once
+#include "common.cuh"
+
+namespace ampc {
+
+constexpr int KT_TILE = 64;       // points per tile (2 x 16-byte loads per lane)
+constexpr int KNN_KMAX = 32;      // top-k list = one entry per lane
+constexpr int KS_WARPS = 4;       // queries (warps) per search CTA
+constexpr int KS_CHUNK = 1024;    // tile lower bounds kept in shared memory per warp
+constexpr int KS_PICKS = 3;       // best-first tile picks before the storage-order sweep
+constexpr int KI_THREADS = 256;   // index kernel: 8 warps = 8 tiles per CTA iteration
+
+struct TileBox { // 32 bytes
+    float lx, ly, lz, hx, hy, hz, pad0, pad1;
+};
+
+struct KnnParams {
+    const float4 *clouds;    // slot s at clouds + s*slot_points
+    const float4 *boxes;     // slot s at boxes + s*slot_tiles*2 (two float4 per tile)
+    const int32_t *counts;   // points held in each slot (after the NaN filter)
+    int64_t slot_points;
+    int64_t slot_tiles;
+    const int32_t *scene_of; // [B] or nullptr (identity)
+    const double *queries;   // [B][Q][3]
+    int32_t Q, k, segs;
+    int32_t *idx;            // [B][Q][k] or nullptr
+    double *dist2;           // [B][Q][k] or nullptr
+    int32_t *count;          // [B][Q] or nullptr
+    double *pts;             // neighbour coordinates, or nullptr
+    int64_t pts_inst_stride; // doubles between instances (lets the caller aim at the NLP prefix)
+    int64_t pts_query_stride;
+    double *ws_d;            // [B][Q][segs][k] partial lists (segs > 1)
+    uint32_t *ws_i;
+};
+
+__device__ __forceinline__ double knn_dist2(double qx, double qy, double qz, float px, float py,
+                                            float pz) {
+    const double d0 = __dsub_rn(qx, (double)px);
+    double r = __dmul_rn(d0, d0);
+    const double d1 = __dsub_rn(qy, (double)py);
+    r = __dadd_rn(r, __dmul_rn(d1, d1));
+    const double d2 = __dsub_rn(qz, (double)pz);
+    r = __dadd_rn(r, __dmul_rn(d2, d2));
+    return r;
+}
+
+// Lower bound of knn_dist2 over every point inside the box (monotone rounding).
+__device__ __forceinline__ double knn_box_lb(double qx, double qy, double qz, float lx, float ly,
+                                             float lz, float hx, float hy, float hz) {
+    const double ax = fmax(fmax(__dsub_rn((double)lx, qx), __dsub_rn(qx, (double)hx)), 0.0);
+    double r = __dmul_rn(ax, ax);
+    const double ay = fmax(fmax(__dsub_rn((double)ly, qy), __dsub_rn(qy, (double)hy)), 0.0);
+    r = __dadd_rn(r, __dmul_rn(ay, ay));
+    const double az = fmax(fmax(__dsub_rn((double)lz, qz), __dsub_rn(qz, (double)hz)), 0.0);
+    r = __dadd_rn(r, __dmul_rn(az, az));
+    return r;
+}
+
+__device__ __forceinline__ float4 knn_ldg(const float4 *p) {
+    return __ldg(p); // ld.global.nc.v4
+}
+
+// ---- order-preserving float <-> uint map so that redux.sync (integer warp
+// reduction, one instruction) yields exact float min / max
+__device__ __forceinline__ unsigned f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ float warp_fmin(float v) {
+    return ord2f(__reduce_min_sync(AMPC_FULL_MASK, f2ord(fminf(v, INFINITY)))); // NaN -> +inf
+}
+__device__ __forceinline__ float warp_fmax(float v) {
+    return ord2f(__reduce_max_sync(AMPC_FULL_MASK, f2ord(fmaxf(v, -INFINITY)))); // NaN -> -inf
+}
+
+__device__ __forceinline__ void tile_box_store(float4 *boxes, int64_t tile, float4 p0, float4 p1,
+                                               bool v0, bool v1, int lane) {
+    const float big = INFINITY;
+    const float x0 = v0 ? p0.x : NAN, y0 = v0 ? p0.y : NAN, z0 = v0 ? p0.z : NAN;
+    const float x1 = v1 ? p1.x : NAN, y1 = v1 ? p1.y : NAN, z1 = v1 ? p1.z : NAN;
+    const float lx = warp_fmin(fminf(fminf(x0, big), fminf(x1, big)));
+    const float ly = warp_fmin(fminf(fminf(y0, big), fminf(y1, big)));
+    const float lz = warp_fmin(fminf(fminf(z0, big), fminf(z1, big)));
+    const float hx = warp_fmax(fmaxf(fmaxf(x0, -big), fmaxf(x1, -big)));
+    const float hy = warp_fmax(fmaxf(fmaxf(y0, -big), fmaxf(y1, -big)));
+    const float hz = warp_fmax(fmaxf(fmaxf(z0, -big), fmaxf(z1, -big)));
+    if (lane == 0) {
+        boxes[2 * tile] = make_float4(lx, ly, lz, hx);
+        boxes[2 * tile + 1] = make_float4(hy, hz, 0.f, 0.f);
+    }
+}
+
+// Index build: one CTA per scene slot; 8 warps x 64 points per iteration.
+// In-place, order-preserving NaN-x removal + tile boxes of the surviving cloud.
+__global__ void __launch_bounds__(KI_THREADS)
+cloud_index_kernel(float4 *clouds, float4 *boxes, int32_t *counts, int64_t slot_points,
+                   int64_t slot_tiles, int first_scene) {
+    const int scene = first_scene + blockIdx.x;
+    float4 *c = clouds + (int64_t)scene * slot_points;
+    float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
+    const int n = counts[scene];
+    __shared__ int sWarp[KI_THREADS / 32];
+    __shared__ int sBase, sDirty;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int PER_IT = (KI_THREADS / 32) * KT_TILE;
+    if (tid == 0) {
+        sBase = 0;
+        sDirty = 0;
+    }
+    __syncthreads();
+    // software prefetch of the next iteration's two records
+    float4 nx0 = make_float4(0, 0, 0, 0), nx1 = nx0;
+    {
+        const int i0 = warp * KT_TILE + lane, i1 = i0 + 32;
+        if (i0 < n) nx0 = c[i0];
+        if (i1 < n) nx1 = c[i1];
+    }
+    for (int start = 0; start < n; start += PER_IT) {
+        const int tb = start + warp * KT_TILE;
+        const int i0 = tb + lane, i1 = i0 + 32;
+        const float4 p0 = nx0, p1 = nx1;
+        {
+            const int j0 = i0 + PER_IT, j1 = i1 + PER_IT;
+            if (j0 < n) nx0 = c[j0];
+            if (j1 < n) nx1 = c[j1];
+        }
+        const bool in0 = i0 < n, in1 = i1 < n;
+        const bool k0 = in0 && !(p0.x != p0.x), k1 = in1 && !(p1.x != p1.x);
+        const unsigned m0 = __ballot_sync(AMPC_FULL_MASK, k0), m1 = __ballot_sync(AMPC_FULL_MASK, k1);
+        const int cw = __popc(m0) + __popc(m1);
+        const int nin = __popc(__ballot_sync(AMPC_FULL_MASK, in0)) + __popc(__ballot_sync(AMPC_FULL_MASK, in1));
+        if (lane == 0)
+            sWarp[warp] = cw;
+        // counts visible; every load of this iteration is complete.  (The prefetch reads
+        // records at >= start + PER_IT, which no write of this iteration can reach.)
+        __syncthreads();
+        int off = sBase, total = 0;
+#pragma unroll
+        for (int w = 0; w < KI_THREADS / 32; ++w) {
+            const int v = sWarp[w];
+            if (w < warp) off += v;
+            total += v;
+        }
+        const bool shifted = (off != tb) || (cw != nin);
+        if (shifted) { // some NaN seen: compact (writes land at or below this iteration's reads)
+            const unsigned lt = (1u << lane) - 1u;
+            if (k0) c[off + __popc(m0 & lt)] = p0;
+            if (k1) c[off + __popc(m0) + __popc(m1 & lt)] = p1;
+            if (lane == 0 && tb < n) sDirty = 1;
+        } else if (tb < n) {
+            tile_box_store(bx, tb / KT_TILE, p0, p1, in0, in1, lane);
+        }
+        __syncthreads();
+        if (tid == 0) sBase += total;
+        __syncthreads();
+    }
+    const int m = sBase;
+    if (tid == 0) counts[scene] = m;
+    if (sDirty) { // rare: rebuild every box from the compacted cloud
+        const int nt = (m + KT_TILE - 1) / KT_TILE;
+        for (int t = warp; t < nt; t += KI_THREADS / 32) {
+            const int i0 = t * KT_TILE + lane, i1 = i0 + 32;
+            float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
+            if (i0 < m) p0 = c[i0];
+            if (i1 < m) p1 = c[i1];
+            tile_box_store(bx, t, p0, p1, i0 < m, i1 < m, lane);
+        }
+    }
+}
+
+// ---- register-resident sorted top-k list: lane j holds entry j -----------------
+struct TopK {
+    double d;
+    uint32_t i;
+};
+__device__ __forceinline__ void topk_insert(TopK &e, int k, double d, uint32_t i, int lane) {
+    const bool before = lane < k && (e.d < d || (e.d == d && e.i < i));
+    const int pos = __popc(__ballot_sync(AMPC_FULL_MASK, before));
+    const double ud = __shfl_up_sync(AMPC_FULL_MASK, e.d, 1);
+    const uint32_t ui = __shfl_up_sync(AMPC_FULL_MASK, e.i, 1);
+    if (lane == pos) {
+        e.d = d;
+        e.i = i;
+    } else if (lane > pos) {
+        e.d = ud;
+        e.i = ui;
+    }
+}
+
+// scan one tile: exact distances of its (up to) 64 points, candidates into the list
+__device__ __forceinline__ void scan_tile(const float4 *cloud, int n, int tile, double qx, double qy,
+                                          double qz, TopK &e, double &kth, int k, int lane) {
+    const int base = tile * KT_TILE;
+    const int i0 = base + lane, i1 = i0 + 32;
+    double d0 = INFINITY, d1 = INFINITY;
+    if (i0 < n) {
+        const float4 p = knn_ldg(cloud + i0);
+        d0 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
+    }
+    if (i1 < n) {
+        const float4 p = knn_ldg(cloud + i1);
+        d1 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
+    }
+    unsigned m0 = __ballot_sync(AMPC_FULL_MASK, i0 < n && d0 <= kth);
+    unsigned m1 = __ballot_sync(AMPC_FULL_MASK, i1 < n && d1 <= kth);
+    while (m0) {
+        const int src = __ffs(m0) - 1;
+        m0 &= m0 - 1;
+        const double d = __shfl_sync(AMPC_FULL_MASK, d0, src);
+        if (d <= kth) {
+            topk_insert(e, k, d, (uint32_t)(base + src), lane);
+            kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        }
+    }
+    while (m1) {
+        const int src = __ffs(m1) - 1;
+        m1 &= m1 - 1;
+        const double d = __shfl_sync(AMPC_FULL_MASK, d1, src);
+        if (d <= kth) {
+            topk_insert(e, k, d, (uint32_t)(base + 32 + src), lane);
+            kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        }
+    }
+}
+
+// SearchForNearest's count rule (kd_tree_two.h:117-124) and the result layout
+__device__ __forceinline__ void knn_write_result(const KnnParams &P, const float4 *cloud, int n,
+                                                 int b, int q, const TopK &e, int lane) {
+    const int k = P.k;
+    const int cnt = (n < k) ? n : (n > k ? k : 0);
+    if (lane < k) {
+        const bool ok = lane < cnt;
+        const int64_t o = ((int64_t)b * P.Q + q) * k + lane;
+        if (P.idx) P.idx[o] = ok ? (int32_t)e.i : -1;
+        if (P.dist2) P.dist2[o] = ok ? e.d : INFINITY;
+        if (P.pts) {
+            double *dst = P.pts + (int64_t)b * P.pts_inst_stride + (int64_t)q * P.pts_query_stride + 3 * lane;
+            if (ok) {
+                const float4 p = knn_ldg(cloud + e.i);
+                dst[0] = (double)p.x;
+                dst[1] = (double)p.y;
+                dst[2] = (double)p.z;
+            } else { // AvoidanceStateMachine.cpp:223-226
+                dst[0] = 10000.0;
+                dst[1] = 10000.0;
+                dst[2] = 10000.0;
+            }
+        }
+    }
+    if (P.count && lane == 0) P.count[(int64_t)b * P.Q + q] = cnt;
+}
+
+// Upper bound of knn_dist2 over every point inside the box (farthest corner).
+__device__ __forceinline__ double knn_box_ub(double qx, double qy, double qz, float lx, float ly,
+                                             float lz, float hx, float hy, float hz) {
+    const double ax = fmax(fabs(__dsub_rn(qx, (double)lx)), fabs(__dsub_rn(qx, (double)hx)));
+    double r = __dmul_rn(ax, ax);
+    const double ay = fmax(fabs(__dsub_rn(qy, (double)ly)), fabs(__dsub_rn(qy, (double)hy)));
+    r = __dadd_rn(r, __dmul_rn(ay, ay));
+    const double az = fmax(fabs(__dsub_rn(qz, (double)lz)), fabs(__dsub_rn(qz, (double)hz)));
+    r = __dadd_rn(r, __dmul_rn(az, az));
+    return r;
+}
+
+__global__ void __launch_bounds__(KS_WARPS * 32)
+knn_search_kernel(const KnnParams P) {
+    __shared__ double sLB[KS_WARPS][KS_CHUNK];       // lower bound per tile of the chunk (NaN = done)
+    __shared__ unsigned short sCand[KS_WARPS][KS_CHUNK]; // compacted list of tiles worth visiting
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y, seg = blockIdx.z;
+    if (q >= P.Q)
+        return;
+    const int k = P.k;
+    const int scene = P.scene_of ? P.scene_of[b] : b;
+    const int n = P.counts[scene];
+    const float4 *cloud = P.clouds + (int64_t)scene * P.slot_points;
+    const float4 *boxes = P.boxes + (int64_t)scene * P.slot_tiles * 2;
+    const double *qp = P.queries + ((int64_t)b * P.Q + q) * 3;
+    const double qx = qp[0], qy = qp[1], qz = qp[2];
+    const int n_tiles = (n + KT_TILE - 1) / KT_TILE;
+    const int n_full = n / KT_TILE; // tiles 0..n_full-1 hold 64 >= k points
+    const int per = (n_tiles + P.segs - 1) / P.segs;
+    const int t_begin = seg * per, t_end = min(n_tiles, t_begin + per);
+    double *lbuf = sLB[warp];
+    unsigned short *cand = sCand[warp];
+    TopK e{INFINITY, 0xffffffffu};
+    // `bound`: no point farther than this can be among the k nearest.  It is the min of
+    // the list's k-th entry and of the farthest-corner distance of any full tile seen
+    // (such a tile alone already holds 64 >= k points within that distance).
+    double bound = INFINITY;
+
+    for (int c0 = t_begin; c0 < t_end; c0 += KS_CHUNK) {
+        const int cn = min(KS_CHUNK, t_end - c0);
+        double ubmin = INFINITY;
+        for (int j = lane; j < cn; j += 32) {
+            const float4 a = knn_ldg(boxes + 2 * (int64_t)(c0 + j));
+            const float4 h = knn_ldg(boxes + 2 * (int64_t)(c0 + j) + 1);
+            lbuf[j] = knn_box_lb(qx, qy, qz, a.x, a.y, a.z, a.w, h.x, h.y);
+            if (c0 + j < n_full)
+                ubmin = fmin(ubmin, knn_box_ub(qx, qy, qz, a.x, a.y, a.z, a.w, h.x, h.y));
+        }
+        bound = fmin(bound, warp_min(ubmin));
+        __syncwarp();
+        // compact the tiles that can still matter
+        int m = 0;
+        for (int j0 = 0; j0 < cn; j0 += 32) {
+            const bool keep = (j0 + lane < cn) && lbuf[j0 + lane] <= bound;
+            const unsigned mk = __ballot_sync(AMPC_FULL_MASK, keep);
+            if (keep)
+                cand[m + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)(j0 + lane);
+            m += __popc(mk);
+        }
+        __syncwarp();
+        // a few best-first picks tighten the bound to (nearly) the true k-th distance ...
+        for (int pick = 0; pick < KS_PICKS; ++pick) {
+            double best = INFINITY;
+            int best_c = -1;
+            for (int c = lane; c < m; c += 32) {
+                const double lb = lbuf[cand[c]];
+                if (lb < best) { // NaN (already visited) never wins
+                    best = lb;
+                    best_c = c;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(AMPC_FULL_MASK, best, o);
+                const int oc = __shfl_xor_sync(AMPC_FULL_MASK, best_c, o);
+                if (ob < best || (ob == best && oc >= 0 && (best_c < 0 || oc < best_c))) {
+                    best = ob;
+                    best_c = oc;
+                }
+            }
+            if (best_c < 0 || !(best <= bound))
+                break;
+            const int j = cand[best_c];
+            double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+            scan_tile(cloud, n, c0 + j, qx, qy, qz, e, kth, k, lane);
+            bound = fmin(bound, kth);
+            if (lane == 0)
+                lbuf[j] = NAN;
+            __syncwarp();
+        }
+        // ... then one sweep over the remaining candidates in storage order
+        for (int cb = 0; cb < m; cb += 32) {
+            const int j = (cb + lane < m) ? (int)cand[cb + lane] : 0;
+            const double lb = (cb + lane < m) ? lbuf[j] : NAN;
+            unsigned mk = __ballot_sync(AMPC_FULL_MASK, lb <= bound);
+            while (mk) {
+                const int src = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const double lbj = __shfl_sync(AMPC_FULL_MASK, lb, src);
+                if (lbj <= bound) { // the bound may have tightened since the ballot
+                    const int jj = __shfl_sync(AMPC_FULL_MASK, j, src);
+                    double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+                    scan_tile(cloud, n, c0 + jj, qx, qy, qz, e, kth, k, lane);
+                    bound = fmin(bound, kth);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (P.segs == 1) {
+        knn_write_result(P, cloud, n, b, q, e, lane);
+    } else if (lane < k) {
+        const int64_t o = ((((int64_t)b * P.Q + q) * P.segs) + seg) * k + lane;
+        P.ws_d[o] = e.d;
+        P.ws_i[o] = e.i;
+    }
+}
+
+// segs > 1: fold the per-segment lists of each (instance, query); one warp each
+__global__ void __launch_bounds__(KS_WARPS * 32)
+knn_merge_kernel(const KnnParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y;
+    if (q >= P.Q)
+        return;
+    const int k = P.k;
+    const int scene = P.scene_of ? P.scene_of[b] : b;
+    const int n = P.counts[scene];
+    const float4 *cloud = P.clouds + (int64_t)scene * P.slot_points;
+    const int64_t o = ((int64_t)b * P.Q + q) * P.segs * k;
+    TopK e{INFINITY, 0xffffffffu};
+    if (lane < k) {
+        e.d = P.ws_d[o + lane];
+        e.i = P.ws_i[o + lane];
+    }
+    for (int s = 1; s < P.segs; ++s)
+        for (int j = 0; j < k; ++j) {
+            const double d = P.ws_d[o + (int64_t)s * k + j];
+            const uint32_t i = P.ws_i[o + (int64_t)s * k + j];
+            const double kd = __shfl_sync(AMPC_FULL_MASK, e.d, k - 1);
+            const uint32_t ki = __shfl_sync(AMPC_FULL_MASK, e.i, k - 1);
+            if (!(d < kd || (d == kd && i < ki)))
+                break; // sorted source: nothing further can enter
+            topk_insert(e, k, d, i, lane);
+        }
+    knn_write_result(P, cloud, n, b, q, e, lane);
+}
+
+} // namespace ampc

@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Headline benchmark: MPC solves/sec at N=20, K=16 obstacle terms/stage, 50k-point clouds.
+
+One "step" = one round of the reference's control tick for a batch of independent MPC
+instances (src/AvoidanceStateMachine.cpp:328-344): Q=N k-NN queries of K neighbours on each
+instance's Obstacle cloud + prefix packing + one NLP solve to convergence (tol 1e-8).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mpc_solves_per_sec"
+UNIT = "solves/s"
+N_H, K_NB, DT = 20, 16, 0.05
+
+
+def workload_name(B, npts):
+    return f"batch={B} MPC instances/GPU, N={N_H}, K={K_NB} obstacle terms/stage, {npts}-pt cloud per instance"
+
+
+# ------------------------------------------------------------------ CPU arm ----
+def cpu_reference(n_scenes: int, npts: int, threads: int, steps: int = 1, warm="ref"):
+    """The reference's CPU path on host cores: tree build + 20x16-NN through the reference's own
+    KDTreeTwo/nanoflann (oracle/_ref, falls back to the C restatement) + the oracle NLP solve.
+    Returns (solves_per_sec_per_step list, description)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import avoid_mpc_b200 as A
+    from oracle import oracle as O
+
+    D, S = A.defaults, A.synth
+    use_ref = O.ref_available()
+    O.lib()
+    if use_ref:
+        O.ref_lib()
+    lb, ub = D.u_bounds()
+    opts = O.default_opts()
+    n_distinct = min(n_scenes, 48)
+    clouds = [S.forest_cloud(10_000 + s, npts)[0] for s in range(n_distinct)]
+    states = [S.states(10_000 + s, N_H) for s in range(n_distinct)]
+
+    def one(i):
+        c = clouds[i % n_distinct]
+        x0, ref, tgt = states[i % n_distinct]
+        tree = O.RefTree(c) if use_ref else O.PortTree(c)       # a1: build (every depth frame)
+        idx, d2, cnt = tree.search(ref[:, :3], K_NB)             # a2/a6: N x K-NN
+        ob = c[idx.reshape(-1), :3].astype(np.float64).reshape(N_H, K_NB, 3)
+        p = S.full_params(S.pack_prefix(x0, ref, ob, tgt))       # a7
+        w, info = O.solve(N_H, K_NB, DT, p, S.warm_start(warm, x0, ref, N_H), lb, ub, opts)  # a8
+        return info.status
+
+    rates = []
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(min(n_scenes, 2 * threads))))  # warm-up
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            list(ex.map(one, range(n_scenes)))
+            rates.append(n_scenes / (time.perf_counter() - t0))
+    kind = "port"
+    desc = (f"{n_scenes} instances/step ({n_distinct} distinct {npts}-pt scenes), {threads} host threads; "
+            f"k-NN = {'reference nanoflann (oracle/_ref)' if use_ref else 'C restatement'} tree build + "
+            f"{N_H}x{K_NB}-NN, NLP = oracle interior-point port (CasADi/IPOPT not installable), tol 1e-8")
+    return rates, kind, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = max(threads * 16, 128)
+    rates, kind, desc = cpu_reference(n, args.npts, threads, steps=args.warmup + args.steps)
+    rates = rates[args.warmup:]
+    v = statistics.mean(rates)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.batch, args.npts), "sample_instances_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm ----
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.p = dev, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import avoid_mpc_b200 as A
+    D, S = A.defaults, A.synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, npts = args.batch, args.npts
+
+    # ---- synthetic inputs (weak scaling: B scenes per GPU, distinct per rank) ----
+    ids = list(range(rank * B, (rank + 1) * B))
+    clouds = S.forest_clouds_torch(ids, npts, dev)                      # (B, npts, 4) f32, resident
+    x0_np, ref_np, _ = S.states_batch(ids, N_H, DT)
+    w0_np = np.stack([S.warm_start(args.warm, x0_np[b], ref_np[b], N_H) for b in range(B)])
+    h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=npts, device=local)
+    h.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+    stream = torch.cuda.current_stream().cuda_stream
+    h.cloud_set_batch_dev(clouds, stream=stream)
+    x0 = torch.tensor(x0_np, device=dev)
+    ref = torch.tensor(ref_np, device=dev)
+    w0 = torch.tensor(w0_np, device=dev)
+    w = torch.empty_like(w0)
+    info = torch.zeros((B, 48), dtype=torch.uint8, device=dev)
+    replan = torch.zeros(B, dtype=torch.int32, device=dev)
+    costs = torch.zeros(B, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+    info_f64 = info.view(torch.float64).view(B, 6)
+
+    def step():
+        w.copy_(w0)
+        # a new depth frame per solve (the reference rebuilds its KD-trees every frame,
+        # src/FrameKDMap.cpp:34-52): index build = the one streaming pass over the cloud
+        h.cloud_index_dev(0, B, stream=stream)
+        h.round_dev(B, x0, ref, w, info_dev=info, replan_dev=replan, speed=D.SPEED,
+                    safety_distance=D.SAFETY_DISTANCE, stream=stream)
+        if world > 1:  # per-instance best-cost exchange: the only collective of the path
+            costs.copy_(info_f64[:, 0])
+            dist.all_gather_into_tensor(gathered, costs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    h.profile_enable(True)
+    l0 = h.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = h.launch_count() - l0
+    prof = h.profile_get()
+    index_ms, knn_ms, solve_ms = prof["index"][0], prof["knn"][0], prof["solve"][0]
+    rounds = prof["solve"][1]
+    h.profile_enable(False)
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    info_np = info.cpu().numpy().view(A.capi.INFO_DTYPE).reshape(B)
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI: clouds + states from pinned host memory,
+    #      trajectories/costs/status back to host, every step ----
+    clouds_h = torch.empty(clouds.shape, dtype=torch.float32, pin_memory=True)
+    clouds_h.copy_(clouds)
+    x0_h = torch.tensor(x0_np).pin_memory()
+    ref_h = torch.tensor(ref_np).pin_memory()
+    w0_h = torch.tensor(w0_np).pin_memory()
+    w_h = torch.empty_like(w0_h).pin_memory()
+    info_h = torch.zeros((B, 48), dtype=torch.uint8).pin_memory()
+    replan_h = torch.zeros(B, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        w_h.copy_(w0_h)
+        h.cloud_set_batch(clouds_h)                                   # H2D of this step's clouds (+ NaN filter)
+        h.round_host_ptrs(B, x0_h, ref_h, w_h, info_h, replan_h, speed=D.SPEED,
+                          safety_distance=D.SAFETY_DISTANCE)          # H2D states, k-NN, solve, D2H results
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / float(t.item())
+    h2d = clouds_h.numel() * 4 + (x0_h.numel() + ref_h.numel() + w_h.numel()) * 8
+    d2h = w_h.numel() * 8 + info_h.numel() + replan_h.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the HBM-bound kernel (k-NN scan): SURVEY.md §8d algorithmic bytes ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    b_knn = 12 * npts + N_H * (24 + K_NB * 12)
+    index_ms_avg = index_ms / max(rounds, 1)
+    knn_ms_avg = knn_ms / max(rounds, 1)
+    stage_ms = index_ms_avg + knn_ms_avg
+    achieved = B * b_knn / (index_ms_avg * 1e-3) / 1e9
+    denom = total_ms if world == 1 else sum(step_ms)
+    roofline = {"kernel": "cloud_index_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": B * b_knn,
+                "as_laid_out_16B_GBps": B * 16 * npts / (index_ms_avg * 1e-3) / 1e9,
+                "avg_launch_ms": index_ms_avg, "step_share": index_ms / denom,
+                "knn_stage": {"what": "index build + box-pruned search (k-NN indices bit-exact)",
+                              "index_ms": index_ms_avg, "search_ms": knn_ms_avg,
+                              "achieved_GBps": B * b_knn / (stage_ms * 1e-3) / 1e9,
+                              "frac": B * b_knn / (stage_ms * 1e-3) / 1e9 / hbm_peak,
+                              "step_share": (index_ms + knn_ms) / denom}}
+    # ---- NLP kernel: FP64 work vs a DGEMM-measured FP64 peak on this box ----
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        a @ a
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        a @ a
+    e1.record()
+    torch.cuda.synchronize()
+    fp64_peak = 5 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    iters = info_np["iters"].astype(np.float64)
+    f_iter = (N_H - 1) * K_NB * 250 + N_H * 4275
+    solve_ms_avg = solve_ms / max(rounds, 1)
+    nlp_tflops = float(iters.sum()) * f_iter / (solve_ms_avg * 1e-3) / 1e12
+    roofline_nlp = {"kernel": "ipm_solve_kernel", "bound": "fp64 latency", "achieved": nlp_tflops, "peak": fp64_peak,
+                    "unit": "TFLOP/s", "frac": nlp_tflops / fp64_peak, "peak_source": "torch f64 matmul 4096^3 on this GPU",
+                    "flop_per_iter": f_iter, "avg_launch_ms": solve_ms_avg,
+                    "step_share": solve_ms / (total_ms if world == 1 else sum(step_ms))}
+
+    # ---- single-instance latency through the host API (cloud resident) ----
+    lat = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        h.round_host_ptrs(1, x0_h, ref_h, w_h, info_h, replan_h, speed=D.SPEED, safety_distance=D.SAFETY_DISTANCE)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat = lat[5:]
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(B, npts), "global_batch": world * B, "warm_start": args.warm,
+                   "tol": args.tol, "max_iter": args.max_iter, "parallelism": f"scene-sharded x{world}",
+                   "l2": "inputs larger than L2 (%.0f MB of clouds per step per GPU)" % (B * npts * 16 / 1e6),
+                   "collective": "all_gather of per-instance costs (NCCL)" if world > 1 else "none"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "note": "every step uploads all clouds from pinned host memory"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "roofline_nlp": roofline_nlp,
+        "latency": {"batch_step_ms_p50": statistics.median(step_ms), "single_instance_round_ms_p50": statistics.median(lat)},
+        "solver": {"converged_frac": float((info_np["status"] == 0).mean()),
+                   "status_counts": np.bincount(info_np["status"], minlength=4).tolist(),
+                   "iters_p50": float(np.median(iters)), "iters_p90": float(np.percentile(iters, 90)),
+                   "iters_max": int(iters.max()), "need_replan_frac": float(replan.float().mean().item())},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n = max(threads * 16, 128)
+        rates, kind, desc = cpu_reference(n, npts, threads, steps=2, warm=args.warm)
+        out["cpu_baseline"] = {"value": rates[-1], "unit": UNIT, "cores": threads, "kind": kind, "sample": desc}
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--npts", type=int, default=50000)
+    ap.add_argument("--warm", default="ref", choices=["ref", "cold"])
+    ap.add_argument("--tol", type=float, default=1e-8)
+    ap.add_argument("--max-iter", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,10 @@ int ampc_cloud_set_batch(ampc_handle *h, int32_t kind, int32_t first_scene, int3
 int ampc_cloud_set_batch_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
                              const void *xyz_dev, const int32_t *counts_host,
                              int64_t scene_stride_bytes, void *stream);
+/* rebuild the index (NaN filter + tile boxes) of clouds already resident in the
+ * handle's slots, e.g. after writing a new depth frame's points in place; async */
+int ampc_cloud_index_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
+                         void *stream);
 /* number of points held for (scene, kind) after the NaN filter (synchronises) */
 int ampc_cloud_count(ampc_handle *h, int32_t scene, int32_t kind, int32_t *n_out);
 
@@ -187,6 +191,11 @@ int ampc_best_of_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_sol
 /* ---- instrumentation ---------------------------------------------------- */
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t ampc_launch_count(const ampc_handle *h);
+/* per-stage device time from CUDA events recorded on the caller's stream around
+ * [0] the cloud index build, [1] the k-NN search, [2] the NLP solve.  enable(1)
+ * resets the totals; get() waits for what was recorded and returns sums and counts. */
+int ampc_profile_enable(ampc_handle *h, int on);
+int ampc_profile_get(ampc_handle *h, double ms_total[3], int64_t launches[3]);
 /* the handle's own stream (void* cudaStream_t) used by the host-buffer calls */
 void *ampc_stream(ampc_handle *h);
 int ampc_synchronize(ampc_handle *h);
