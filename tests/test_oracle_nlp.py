@@ -1,0 +1,152 @@
+"""CPU: the NLP oracle.  Functions against the golden values (torch.autograd float64
+re-derivation of tools/mpc_obstacle_casadi.py) and against autograd live; the solve
+against scipy on the same NLP.  CasADi/IPOPT cannot be installed here: parity with the
+reference's third-party solver is UNPINNED and is defined at convergence."""
+import os
+
+import numpy as np
+import pytest
+
+import avoid_mpc_b200 as A
+from oracle import oracle as O
+import torch_nlp
+
+D, S = A.defaults, A.synth
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "nlp_golden.npz"))
+REL = 1e-12  # function / derivative parity, relative to the largest entry
+
+
+def _full_hessian(N, Hx, Hu):
+    H = np.zeros((10 + 14 * N,) * 2)
+    for k in range(N):
+        a = 14 * (k + 1)
+        H[a:a + 10, a:a + 10] = Hx[k]
+        b = 14 * k + 10
+        H[b:b + 4, b:b + 4] = np.diag(Hu)
+    return H
+
+
+@pytest.mark.parametrize("tag", ["cyl", "yaw"])
+def test_functions_match_autograd_golden(tag):
+    N, K = int(GOLD[tag + "_N"]), int(GOLD[tag + "_K"])
+    w, p = GOLD[tag + "_w"], GOLD[tag + "_p"]
+    assert w.size == O.nw(N) and p.size == O.np_(N, K)
+    f = O.f(N, K, w, p)
+    assert abs(f - float(GOLD[tag + "_f"])) <= REL * abs(f)
+    g = O.grad_f(N, K, w, p)
+    assert np.abs(g - GOLD[tag + "_grad"]).max() <= REL * np.abs(g).max()
+    H = _full_hessian(N, *O.hess_f(N, K, w, p))
+    assert np.abs(H - GOLD[tag + "_hess"]).max() <= REL * np.abs(H).max()
+
+
+def test_functions_match_autograd_live():
+    rng = np.random.default_rng(5)
+    N, K = 6, 4
+    x0, ref, tgt = S.states(9, N, 1.0 / N)
+    ref[:, 3] = rng.uniform(-2, 2, N)
+    ob = ref[:, None, :3] + rng.normal(0, 0.4, (N, K, 3))
+    p = S.full_params(S.pack_prefix(x0, ref, ob, tgt))
+    w = rng.normal(0, 1, O.nw(N))
+    f, g, H = torch_nlp.f_grad_hess(N, K, w, p)
+    assert abs(O.f(N, K, w, p) - f) <= REL * abs(f)
+    assert np.abs(O.grad_f(N, K, w, p) - g).max() <= REL * np.abs(g).max()
+    assert np.abs(_full_hessian(N, *O.hess_f(N, K, w, p)) - H).max() <= REL * np.abs(H).max()
+
+
+def test_dimensions_and_constraints():
+    # mpc_obstacle_casadi.py:76-85,158,160,217,219
+    assert O.nw(20) == 290 and O.ng(20) == 210 and O.np_(20, 16) == 1214 and O.np_(30, 3) == 624
+    N, K, dt = 20, 8, 0.05
+    rng = np.random.default_rng(2)
+    x0, ref, tgt = S.states(1, N)
+    p = S.full_params(S.pack_prefix(x0, ref, rng.normal(size=(N, K, 3)), tgt))
+    w = rng.normal(size=O.nw(N))
+    Phi, Gam, gam = O.dyn_matrices(D.TAU, dt)
+    X = np.array([w[14 * k:14 * k + 10] for k in range(N + 1)])
+    U = np.array([w[14 * k + 10:14 * k + 14] for k in range(N)])
+    g2 = np.concatenate([X[0] - x0] + [Phi @ X[k] + Gam @ U[k] + gam - X[k + 1] for k in range(N)])
+    assert np.abs(O.g(N, K, w, p, dt) - g2).max() < 1e-13
+    # RK4 x 4 is NOT the matrix exponential: entries differ by ~5e-6
+    from scipy.linalg import expm
+    Ac = np.zeros((10, 10))
+    for i in range(3):
+        Ac[i, 4 + i] = 1
+        Ac[4 + i, 7 + i] = 1
+        Ac[7 + i, 7 + i] = -D.TAU[i]
+    diff = np.abs(expm(Ac * dt) - Phi).max()
+    assert 1e-7 < diff < 1e-4
+
+
+def test_cylinder_fixture_optimum_is_stable():
+    """The reference's own smoke scene (mpc_obstacle_casadi.py:448-498)."""
+    N, K, dt = int(GOLD["cyl_N"]), int(GOLD["cyl_K"]), float(GOLD["cyl_dt"])
+    w, info = O.solve(N, K, dt, GOLD["cyl_p"], GOLD["cyl_w0"], GOLD["cyl_lb"], GOLD["cyl_ub"])
+    assert info.status == 0 and info.kkt_dual <= 1e-8 and info.kkt_compl <= 1e-8
+    assert np.abs(w - GOLD["cyl_wstar"]).max() < 1e-9
+    assert abs(info.cost - float(GOLD["cyl_cost"])) < 1e-9 * abs(info.cost)
+    assert abs(O.f(N, K, w, GOLD["cyl_p"]) - info.cost) < 1e-9 * abs(info.cost)
+    assert np.abs(O.g(N, K, w, GOLD["cyl_p"], dt)).max() < 1e-10
+
+
+def _reduced(N, K, dt, p, x0):
+    """J(U) = f(rollout(U), U) and its gradient by the adjoint, from the oracle's functions."""
+    Phi, Gam, gam = O.dyn_matrices(p[-30:-26], dt)
+
+    def unpack(U):
+        U = U.reshape(N, 4)
+        w = np.zeros(O.nw(N))
+        x = x0.copy()
+        w[0:10] = x
+        for k in range(N):
+            w[14 * k + 10:14 * k + 14] = U[k]
+            x = Phi @ x + Gam @ U[k] + gam
+            w[14 * (k + 1):14 * (k + 1) + 10] = x
+        return w
+
+    def fun(U):
+        w = unpack(U)
+        g = O.grad_f(N, K, w, p)
+        lam = np.zeros(10)
+        gu = np.zeros((N, 4))
+        for k in range(N - 1, -1, -1):
+            lam = g[14 * (k + 1):14 * (k + 1) + 10] + (Phi.T @ lam if k < N - 1 else 0)
+            gu[k] = g[14 * k + 10:14 * k + 14] + Gam.T @ lam
+        return O.f(N, K, w, p), gu.ravel()
+
+    return fun, unpack
+
+
+@pytest.mark.parametrize("sid", [0, 13, 15])
+def test_converged_optimum_matches_scipy(sid):
+    """Same NLP, independent solver (scipy L-BFGS-B on the control-space problem with the
+    box bounds).  Scenes whose optimum is smooth (no |v.n| kink active)."""
+    from scipy.optimize import minimize
+    N, K, dt = 20, 16, 0.05
+    c, _ = S.forest_cloud(sid, 10000)
+    x0, ref, tgt = S.states(sid, N)
+    idx, d2, cnt = O.knn_bruteforce(c, ref[:, :3], K)
+    p = S.full_params(S.pack_prefix(x0, ref, c[idx][:, :, :3].astype(np.float64), tgt))
+    lb, ub = D.u_bounds()
+    w, info = O.solve(N, K, dt, p, S.warm_start("ref", x0, ref, N), lb, ub)
+    assert info.status == 0
+    fun, unpack = _reduced(N, K, dt, p, x0)
+    U0 = np.tile([0, 0, 9.81, 0.0], N)
+    r = minimize(fun, U0, jac=True, method="L-BFGS-B", bounds=list(zip(np.tile(lb, N), np.tile(ub, N))),
+                 options=dict(maxiter=5000, ftol=1e-16, gtol=1e-9, maxcor=50))
+    ws = unpack(r.x)
+    assert abs(r.fun - info.cost) <= 1e-7 * abs(info.cost)
+    assert np.abs(ws - w).max() < 1e-4  # north-star trajectory tolerance
+
+
+def test_warm_starts_agree_and_status_codes():
+    N, K, dt = 20, 16, 0.05
+    lb, ub = D.u_bounds()
+    c, _ = S.forest_cloud(1, 10000)
+    x0, ref, tgt = S.states(1, N)
+    idx, _, _ = O.knn_bruteforce(c, ref[:, :3], K)
+    p = S.full_params(S.pack_prefix(x0, ref, c[idx][:, :, :3].astype(np.float64), tgt))
+    wc, ic = O.solve(N, K, dt, p, S.warm_start("cold", x0, ref, N), lb, ub)
+    wr, ir = O.solve(N, K, dt, p, S.warm_start("ref", x0, ref, N), lb, ub)
+    assert ic.status == 0 and ir.status == 0 and np.abs(wc - wr).max() < 1e-6
+    _, i2 = O.solve(N, K, dt, p, S.warm_start("cold", x0, ref, N), lb, ub, O.default_opts(max_iter=3))
+    assert i2.status == 1 and i2.iters == 3
