@@ -61,6 +61,11 @@ def build(verbose: bool = False) -> str:
         print(r.stdout, r.stderr)
     if r.returncode:
         raise RuntimeError("building libampc.so failed")
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "host")], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout, r.stderr)
+    if r.returncode:
+        raise RuntimeError("building the C++ host shim failed")
     return LIB_PATH
 
 
