@@ -33,7 +33,7 @@ namespace ampc {
 
 // per-warp shared-memory layout, in doubles
 struct WarpLayout {
-    int x, u, zl, zu, dx, du, q, r, rt, rdiag, Hc, Kg, kf, P, PA, PB, Bm, S, pv, lam, b, cs, total;
+    int x, u, zl, zu, dx, du, q, r, rt, rdiag, Hc, Kg, kf, cs, total;
     __host__ __device__ explicit WarpLayout(int N) {
         int o = 0;
         x = o, o += (N + 1) * 10;
@@ -47,16 +47,8 @@ struct WarpLayout {
         rt = o, o += N * 4;
         rdiag = o, o += N * 4;
         Hc = o, o += N * 21; // stage k (1..N-1) at (k-1)*21: pp(6) pv(9) vv(6)
-        Kg = o, o += N * 40;
+        Kg = o, o += N * 48; // feedback gains: [k][component 0..2][chain-pair lane 0..15]
         kf = o, o += N * 4;
-        P = o, o += 100;
-        PA = o, o += 100;
-        PB = o, o += 40;
-        Bm = o, o += 40;
-        S = o, o += 16;
-        pv = o, o += 10;
-        lam = o, o += 10;
-        b = o, o += 4;
         cs = o, o += N * 2;
         total = (o + 1) & ~1;
     }
@@ -66,33 +58,44 @@ __host__ __device__ inline size_t solve_smem_bytes(int N, int warps) {
     return sizeof(SolveConsts) + 128 + (size_t)warps * WarpLayout(N).total * sizeof(double);
 }
 
-// ---- sparse products with the chain-structured Phi (10x10) and Gam (10x4).
-// State order [p(0..2), yaw(3), v(4..6), a(7..9)].  Column j of Phi has
-// non-zeros at rows {j} (+ {j-4} for v, + {j-3, j-7} for a); column j of Gam at
-// rows {j, 4+j, 7+j} (j < 3) or {3} (j = 3).  (mpc_obstacle_casadi.py:106-122)
+// ---- chain structure.  State order [p(0..2), yaw(3), v(4..6), a(7..9)]; the affine
+// dynamics (mpc_obstacle_casadi.py:106-122) decouple into four chains: axis i < 3 with
+// components (p_i, v_i, a_i) = state indices (i, 4+i, 7+i) driven by control i, and yaw
+// (component 0 = state 3; components 1,2 are padding that stays exactly zero).  Chain i
+// advances by the upper-triangular 3x3 matrix F_i and the 3-vector G_i below.
+struct Chain {
+    double d1, c1, c2, d2, c3, c4; // F = [[d1,c1,c2],[0,d2,c3],[0,0,c4]]
+    double g1, g2, g3;             // G
+};
+__device__ __forceinline__ Chain load_chain(const double *Phi, const double *Gam, int i) {
+    Chain c;
+    if (i < 3) {
+        c.d1 = Phi[i * 10 + i], c.c1 = Phi[i * 10 + 4 + i], c.c2 = Phi[i * 10 + 7 + i];
+        c.d2 = Phi[(4 + i) * 10 + 4 + i], c.c3 = Phi[(4 + i) * 10 + 7 + i];
+        c.c4 = Phi[(7 + i) * 10 + 7 + i];
+        c.g1 = Gam[i * 4 + i], c.g2 = Gam[(4 + i) * 4 + i], c.g3 = Gam[(7 + i) * 4 + i];
+    } else {
+        c.d1 = Phi[33], c.c1 = c.c2 = c.d2 = c.c3 = c.c4 = 0.0;
+        c.g1 = Gam[15], c.g2 = c.g3 = 0.0;
+    }
+    return c;
+}
+// state index of component c of chain i (-1: padding)
+__device__ __forceinline__ int chain_state(int i, int c) {
+    return i < 3 ? (c == 0 ? i : (c == 1 ? 4 + i : 7 + i)) : (c == 0 ? 3 : -1);
+}
+// y = F' x   and   y = F x
+__device__ __forceinline__ void chain_FT(const Chain &f, const double x[3], double y[3]) {
+    y[0] = f.d1 * x[0];
+    y[1] = f.c1 * x[0] + f.d2 * x[1];
+    y[2] = f.c2 * x[0] + f.c3 * x[1] + f.c4 * x[2];
+}
+__device__ __forceinline__ void chain_F(const Chain &f, const double x[3], double u, double y[3]) {
+    y[0] = f.d1 * x[0] + f.c1 * x[1] + f.c2 * x[2] + f.g1 * u;
+    y[1] = f.d2 * x[1] + f.c3 * x[2] + f.g2 * u;
+    y[2] = f.c4 * x[2] + f.g3 * u;
+}
 
-// sum_l Phi[l][i] * v[l*stride]
-__device__ __forceinline__ double phiT_dot(const double *Phi, int i, const double *v, int stride) {
-    double a = Phi[i * 10 + i] * v[i * stride];
-    if (i >= 4 && i <= 6)
-        a += Phi[(i - 4) * 10 + i] * v[(i - 4) * stride];
-    if (i >= 7) {
-        a += Phi[(i - 3) * 10 + i] * v[(i - 3) * stride];
-        a += Phi[(i - 7) * 10 + i] * v[(i - 7) * stride];
-    }
-    return a;
-}
-// sum_l row[l] * Phi[l][j]
-__device__ __forceinline__ double dot_phi(const double *Phi, const double *row, int j) {
-    double a = row[j] * Phi[j * 10 + j];
-    if (j >= 4 && j <= 6)
-        a += row[j - 4] * Phi[(j - 4) * 10 + j];
-    if (j >= 7) {
-        a += row[j - 3] * Phi[(j - 3) * 10 + j];
-        a += row[j - 7] * Phi[(j - 7) * 10 + j];
-    }
-    return a;
-}
 // sum_l Phi[i][l] * v[l]   (row i of Phi: cols {i} + {i+4, i+7} for p, {i+3} for v)
 __device__ __forceinline__ double phi_row_dot(const double *Phi, int i, const double *v) {
     double a = Phi[i * 10 + i] * v[i];
@@ -104,13 +107,6 @@ __device__ __forceinline__ double phi_row_dot(const double *Phi, int i, const do
     }
     return a;
 }
-// sum_l Gam[l][j] * v[l*stride]
-__device__ __forceinline__ double gamT_dot(const double *Gam, int j, const double *v, int stride) {
-    if (j == 3)
-        return Gam[3 * 4 + 3] * v[3 * stride];
-    return Gam[j * 4 + j] * v[j * stride] + Gam[(4 + j) * 4 + j] * v[(4 + j) * stride] +
-           Gam[(7 + j) * 4 + j] * v[(7 + j) * stride];
-}
 // sum_l Gam[i][l] * u[l]   (row i of Gam has one non-zero)
 __device__ __forceinline__ double gam_row_dot(const double *Gam, int i, const double *u) {
     const int j = (i < 3) ? i : (i == 3 ? 3 : (i < 7 ? i - 4 : i - 7));
@@ -119,19 +115,6 @@ __device__ __forceinline__ double gam_row_dot(const double *Gam, int i, const do
 
 __device__ __forceinline__ int sym3(int a, int b) { // a <= b in 0..2 -> 0..5
     return a * 3 - (a * (a - 1)) / 2 + (b - a);
-}
-
-// Hessian entry (i <= j) of stage k's cost from the compact (p,v)-block store.
-__device__ __forceinline__ double stage_hess(const double *Hc, const double *qp, int i, int j) {
-    const bool ip = i < 3, iv = (i >= 4 && i <= 6);
-    const bool jp = j < 3, jv = (j >= 4 && j <= 6);
-    if (ip && jp)
-        return Hc[sym3(i, j)];
-    if (ip && jv)
-        return Hc[6 + i * 3 + (j - 4)];
-    if (iv && jv)
-        return Hc[15 + sym3(i - 4, j - 4)];
-    return (i == j) ? 2.0 * qp[i] : 0.0;
 }
 
 struct WarpCtx {
@@ -297,189 +280,209 @@ __device__ double eval_cost(const WarpCtx &w, double alpha, double eps) {
     return warp_sum(acc);
 }
 
-// Riccati backward sweep + adjoint; returns false if some S_k is not positive
-// definite (the reduced Hessian has the wrong inertia) -> caller regularises.
-// Also returns the dual infeasibility |r_k + Gam'lam_{k+1} - zl + zu|_inf.
+// Riccati backward sweep + adjoint.  Lane 4i+j (i,j = chains, lanes 16..31 mirror 0..15)
+// keeps the 3x3 block P^(ij) coupling chain i and chain j in registers; per stage
+//   S_ij = G_i' P^(ij) G_j (+R_i),  Bm^(i)_j = F_i' P^(ij) G_j,  A^(ij) = F_i' P^(ij) F_j,
+//   P^(ij) <- Q^(ij) + A^(ij) - Bm^(i) S^-1 Bm^(j)',
+// with S gathered by shuffles (it is 3x3 + the decoupled yaw scalar) and factored as LDL'
+// redundantly in every lane.  Returns false if a pivot of S is not positive (the reduced
+// Hessian has the wrong inertia) -> the caller regularises.  Also returns the dual
+// infeasibility |r_k + G'lam_{k+1} - zl + zu|_inf.
 __device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_out) {
     const SolveConsts &c = *w.c;
-    const int N = c.N, lane = w.lane;
+    const int N = c.N;
     double *s = w.s;
     const WarpLayout &L = w.L;
-    const double *Phi = c.Phi, *Gam = c.Gam;
+    const int pl = w.lane & 15, ci = pl >> 2, cj = pl & 3;
+    const Chain fi = load_chain(c.Phi, c.Gam, ci), fj = load_chain(c.Phi, c.Gam, cj);
     const double *qg = c.wgt, *qp = c.wgt + 10;
-    double *P = s + L.P, *PA = s + L.PA, *PB = s + L.PB, *Bm = s + L.Bm, *S = s + L.S;
-    double *pv = s + L.pv, *lam = s + L.lam, *bb = s + L.b;
+    const int si0 = chain_state(ci, 0), si1 = chain_state(ci, 1), si2 = chain_state(ci, 2);
+    const bool diag = ci == cj, real = ci < 3 && cj < 3;
+    const int lo = ci < cj ? ci : cj, hi = ci < cj ? cj : ci;
     // terminal: P_N = diag(2 Q_goal) + delta, p_N = lam_N = q_N
-    for (int e = lane; e < 100; e += 32) {
-        const int i = e / 10, j = e - 10 * i;
-        P[e] = (i == j) ? 2.0 * qg[i] + delta : 0.0;
+    double P[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double pv[3] = {0, 0, 0}, lv[3];
+    if (diag) {
+        P[0] = 2.0 * qg[si0] + delta;
+        if (ci < 3) {
+            P[4] = 2.0 * qg[si1] + delta;
+            P[8] = 2.0 * qg[si2] + delta;
+        }
     }
-    if (lane < 10) {
-        pv[lane] = s[L.q + 10 * N + lane];
-        lam[lane] = pv[lane];
+    pv[0] = s[L.q + 10 * N + si0];
+    if (ci < 3) {
+        pv[1] = s[L.q + 10 * N + si1];
+        pv[2] = s[L.q + 10 * N + si2];
     }
-    __syncwarp();
+    lv[0] = pv[0], lv[1] = pv[1], lv[2] = pv[2];
     double e_dual = 0.0;
     bool ok = true;
     for (int k = N - 1; k >= 0; --k) {
-        // (1) PA = P Phi, PB = P Gam
-        for (int e = lane; e < 100; e += 32) {
-            const int i = e / 10, j = e - 10 * i;
-            PA[e] = dot_phi(Phi, P + 10 * i, j);
+        // (1) products with this lane's block
+        double t[3], bm[3], M[9], A[9];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+            t[a] = P[3 * a] * fj.g1 + P[3 * a + 1] * fj.g2 + P[3 * a + 2] * fj.g3;
+        double Sij = fi.g1 * t[0] + fi.g2 * t[1] + fi.g3 * t[2];
+        if (diag)
+            Sij += s[L.rdiag + 4 * k + ci] + delta;
+        chain_FT(fi, t, bm);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            M[3 * a] = fj.d1 * P[3 * a];
+            M[3 * a + 1] = fj.c1 * P[3 * a] + fj.d2 * P[3 * a + 1];
+            M[3 * a + 2] = fj.c2 * P[3 * a] + fj.c3 * P[3 * a + 1] + fj.c4 * P[3 * a + 2];
         }
-        for (int e = lane; e < 40; e += 32) {
-            const int i = e >> 2, j = e & 3;
-            const double *row = P + 10 * i;
-            PB[e] = (j == 3) ? row[3] * Gam[15]
-                             : row[j] * Gam[j * 4 + j] + row[4 + j] * Gam[(4 + j) * 4 + j] +
-                                   row[7 + j] * Gam[(7 + j) * 4 + j];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            A[b] = fi.d1 * M[b];
+            A[3 + b] = fi.c1 * M[b] + fi.d2 * M[3 + b];
+            A[6 + b] = fi.c2 * M[b] + fi.c3 * M[3 + b] + fi.c4 * M[6 + b];
         }
-        __syncwarp();
-        // (2) Bm = Phi' PB (10x4), S = R + Gam' PB (4x4), b = rt + Gam' pv ;
-        //     reduced gradient and adjoint for the KKT error
-        for (int e = lane; e < 40; e += 32) {
-            const int i = e >> 2, j = e & 3;
-            Bm[e] = phiT_dot(Phi, i, PB + j, 4);
+        const double bi = s[L.rt + 4 * k + ci] + fi.g1 * pv[0] + fi.g2 * pv[1] + fi.g3 * pv[2];
+        if (diag) {
+            const double gu = s[L.r + 4 * k + ci] + fi.g1 * lv[0] + fi.g2 * lv[1] + fi.g3 * lv[2];
+            e_dual = fmax(e_dual, fabs(gu - s[L.zl + 4 * k + ci] + s[L.zu + 4 * k + ci]));
         }
-        if (lane < 16) {
-            const int i = lane >> 2, j = lane & 3;
-            double a = gamT_dot(Gam, i, PB + j, 4);
-            if (i == j)
-                a += s[L.rdiag + 4 * k + i] + delta;
-            S[lane] = a;
-        } else if (lane < 20) {
-            const int i = lane - 16;
-            bb[i] = s[L.rt + 4 * k + i] + gamT_dot(Gam, i, pv, 1);
-        } else if (lane < 24) {
-            const int i = lane - 20;
-            const double gu = s[L.r + 4 * k + i] + gamT_dot(Gam, i, lam, 1);
-            e_dual = fmax(e_dual, fabs(gu - s[L.zl + 4 * k + i] + s[L.zu + 4 * k + i]));
-        }
-        __syncwarp();
-        // (3) S = L D L' in registers (all lanes), inertia check, solve for gains
-        const double d0 = S[0];
-        const double i0 = 1.0 / d0;
-        const double l10 = S[4] * i0, l20 = S[8] * i0, l30 = S[12] * i0;
-        const double d1 = S[5] - l10 * l10 * d0;
-        const double i1 = 1.0 / d1;
-        const double l21 = (S[9] - l20 * l10 * d0) * i1, l31 = (S[13] - l30 * l10 * d0) * i1;
-        const double d2 = S[10] - l20 * l20 * d0 - l21 * l21 * d1;
-        const double i2 = 1.0 / d2;
-        const double l32 = (S[14] - l30 * l20 * d0 - l31 * l21 * d1) * i2;
-        const double d3 = S[15] - l30 * l30 * d0 - l31 * l31 * d1 - l32 * l32 * d2;
-        const double i3 = 1.0 / d3;
-        if (!(d0 > 0.0) || !(d1 > 0.0) || !(d2 > 0.0) || !(d3 > 0.0)) {
+        // (2) S = L D L' (3x3 for the axes + the yaw scalar), every lane redundantly
+        const double S00 = __shfl_sync(AMPC_FULL_MASK, Sij, 0), S10 = __shfl_sync(AMPC_FULL_MASK, Sij, 4);
+        const double S20 = __shfl_sync(AMPC_FULL_MASK, Sij, 8), S11 = __shfl_sync(AMPC_FULL_MASK, Sij, 5);
+        const double S21 = __shfl_sync(AMPC_FULL_MASK, Sij, 9), S22 = __shfl_sync(AMPC_FULL_MASK, Sij, 10);
+        const double S33 = __shfl_sync(AMPC_FULL_MASK, Sij, 15);
+        const double d0 = S00, i0 = 1.0 / d0, i3 = 1.0 / S33;
+        const double l10 = S10 * i0, l20 = S20 * i0;
+        const double d1 = S11 - l10 * l10 * d0, i1 = 1.0 / d1;
+        const double l21 = (S21 - l20 * l10 * d0) * i1;
+        const double d2 = S22 - l20 * l20 * d0 - l21 * l21 * d1, i2 = 1.0 / d2;
+        if (!(d0 > 0.0) || !(d1 > 0.0) || !(d2 > 0.0) || !(S33 > 0.0)) {
             ok = false;
             break; // uniform: every lane computed the same pivots
         }
-        if (lane <= 10) { // columns 0..9 of -Bm' and column 10 = -b
-            double b0, b1, b2, b3;
-            if (lane < 10) {
-                b0 = -Bm[lane * 4 + 0], b1 = -Bm[lane * 4 + 1], b2 = -Bm[lane * 4 + 2],
-                b3 = -Bm[lane * 4 + 3];
-            } else {
-                b0 = -bb[0], b1 = -bb[1], b2 = -bb[2], b3 = -bb[3];
-            }
-            const double w0 = b0;
-            const double w1 = b1 - l10 * w0;
-            const double w2 = b2 - l20 * w0 - l21 * w1;
-            const double w3 = b3 - l30 * w0 - l31 * w1 - l32 * w2;
-            const double y3 = w3 * i3;
-            const double y2 = w2 * i2 - l32 * y3;
-            const double y1 = w1 * i1 - l21 * y2 - l31 * y3;
-            const double y0 = w0 * i0 - l10 * y1 - l20 * y2 - l30 * y3;
-            if (lane < 10) {
-                double *Kg = s + L.Kg + 40 * k;
-                Kg[0 * 10 + lane] = y0;
-                Kg[1 * 10 + lane] = y1;
-                Kg[2 * 10 + lane] = y2;
-                Kg[3 * 10 + lane] = y3;
-            } else {
-                double *kf = s + L.kf + 4 * k;
-                kf[0] = y0, kf[1] = y1, kf[2] = y2, kf[3] = y3;
-            }
+        // feed-forward kff = -S^-1 b  (b_l lives in lanes 5l)
+        double kff[4];
+        {
+            const double b0 = -__shfl_sync(AMPC_FULL_MASK, bi, 0), b1 = -__shfl_sync(AMPC_FULL_MASK, bi, 5);
+            const double b2 = -__shfl_sync(AMPC_FULL_MASK, bi, 10), b3 = -__shfl_sync(AMPC_FULL_MASK, bi, 15);
+            const double w1 = b1 - l10 * b0, w2 = b2 - l20 * b0 - l21 * w1;
+            kff[2] = w2 * i2;
+            kff[1] = w1 * i1 - l21 * kff[2];
+            kff[0] = b0 * i0 - l10 * kff[1] - l20 * kff[2];
+            kff[3] = b3 * i3;
         }
-        __syncwarp();
+        if (w.lane < 4)
+            s[L.kf + 4 * k + w.lane] = w.lane == 0 ? kff[0] : (w.lane == 1 ? kff[1] : (w.lane == 2 ? kff[2] : kff[3]));
         if (k == 0)
-            break;
-        // (4) P_k = Q_k + delta I + Phi' PA + Bm Kg (upper triangle, mirrored),
-        //     p_k = q_k + Phi' pv + Bm kf,  lam_k = q_k + Phi' lam_{k+1}
-        const double *Kg = s + L.Kg + 40 * k, *kf = s + L.kf + 4 * k;
+            break; // dx_0 = 0: no feedback gain and no P_0 needed
+        // (3) Y = S^-1 Bm^(j)'  (4 controls x 3 components of chain j) and Bm^(i)
+        double Y[4][3], Bi[3][4];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) {
+            const double r0 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 0);
+            const double r1 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 1);
+            const double r2 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 2);
+            const double r3 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 3);
+            const double w1 = r1 - l10 * r0, w2 = r2 - l20 * r0 - l21 * w1;
+            Y[2][cc] = w2 * i2;
+            Y[1][cc] = w1 * i1 - l21 * Y[2][cc];
+            Y[0][cc] = r0 * i0 - l10 * Y[1][cc] - l20 * Y[2][cc];
+            Y[3][cc] = r3 * i3;
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+                Bi[cc][l] = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * ci + l);
+        }
+        // feedback gain of control i on chain j: K = -Y[i][.]
+        if (w.lane < 16) {
+            double *Kg = s + L.Kg + 48 * k;
+            const double y0 = ci == 0 ? Y[0][0] : (ci == 1 ? Y[1][0] : (ci == 2 ? Y[2][0] : Y[3][0]));
+            const double y1 = ci == 0 ? Y[0][1] : (ci == 1 ? Y[1][1] : (ci == 2 ? Y[2][1] : Y[3][1]));
+            const double y2 = ci == 0 ? Y[0][2] : (ci == 1 ? Y[1][2] : (ci == 2 ? Y[2][2] : Y[3][2]));
+            Kg[pl] = -y0;
+            Kg[16 + pl] = -y1;
+            Kg[32 + pl] = -y2;
+        }
+        // (4) P^(ij) <- Q^(ij) + A - Bm^(i) Y ;  p^(i) <- q^(i) + F_i' p^(i) + Bm^(i) kff ;
+        //     lam^(i) <- q^(i) + F_i' lam^(i)
         const double *Hc = s + L.Hc + 21 * (k - 1);
-        double pn = 0.0, ln = 0.0;
-        if (lane < 10) {
-            const double qk = s[L.q + 10 * k + lane];
-            pn = qk + phiT_dot(Phi, lane, pv, 1) + Bm[lane * 4 + 0] * kf[0] +
-                 Bm[lane * 4 + 1] * kf[1] + Bm[lane * 4 + 2] * kf[2] + Bm[lane * 4 + 3] * kf[3];
-            ln = qk + phiT_dot(Phi, lane, lam, 1);
-        }
-        double pe[2];
-        int pi_[2], pj_[2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m) {
-            const int e = lane + 32 * m; // 55 upper-triangular entries
-            pi_[m] = -1;
-            if (e < 55) {
-                int i = 0, rem = e;
-                while (rem >= 10 - i) {
-                    rem -= 10 - i;
-                    ++i;
-                }
-                const int j = i + rem;
-                double a = stage_hess(Hc, qp, i, j) + (i == j ? delta : 0.0);
-                a += phiT_dot(Phi, i, PA + j, 10);
-                a += Bm[i * 4 + 0] * Kg[0 * 10 + j] + Bm[i * 4 + 1] * Kg[1 * 10 + j] +
-                     Bm[i * 4 + 2] * Kg[2 * 10 + j] + Bm[i * 4 + 3] * Kg[3 * 10 + j];
-                pe[m] = a;
-                pi_[m] = i;
-                pj_[m] = j;
+        double Qb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (real) {
+            Qb[0] = Hc[sym3(lo, hi)];
+            Qb[1] = Hc[6 + ci * 3 + cj];
+            Qb[3] = Hc[6 + cj * 3 + ci];
+            Qb[4] = Hc[15 + sym3(lo, hi)];
+            if (diag) {
+                Qb[8] = 2.0 * qp[si2];
+                Qb[0] += delta, Qb[4] += delta, Qb[8] += delta;
             }
+        } else if (diag) { // yaw
+            Qb[0] = 2.0 * qp[3] + delta;
         }
-        __syncwarp(); // all reads of P, pv, lam done
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
-            if (pi_[m] >= 0) {
-                P[pi_[m] * 10 + pj_[m]] = pe[m];
-                P[pj_[m] * 10 + pi_[m]] = pe[m];
-            }
-        if (lane < 10) {
-            pv[lane] = pn;
-            lam[lane] = ln;
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                P[3 * a + b] = Qb[3 * a + b] + A[3 * a + b] - (Bi[a][0] * Y[0][b] + Bi[a][1] * Y[1][b] +
+                                                               Bi[a][2] * Y[2][b] + Bi[a][3] * Y[3][b]);
+        double qk[3] = {s[L.q + 10 * k + si0], 0.0, 0.0};
+        if (ci < 3) {
+            qk[1] = s[L.q + 10 * k + si1];
+            qk[2] = s[L.q + 10 * k + si2];
         }
-        __syncwarp();
+        double fp[3], fl[3];
+        chain_FT(fi, pv, fp);
+        chain_FT(fi, lv, fl);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            pv[a] = qk[a] + fp[a] + Bi[a][0] * kff[0] + Bi[a][1] * kff[1] + Bi[a][2] * kff[2] + Bi[a][3] * kff[3];
+            lv[a] = qk[a] + fl[a];
+        }
     }
+    __syncwarp();
     ok = __all_sync(AMPC_FULL_MASK, ok);
     *e_dual_out = warp_max(e_dual);
     return ok;
 }
 
-// forward sweep: du_k = Kg_k dx_k + kf_k, dx_{k+1} = Phi dx_k + Gam du_k, dx_0 = 0
+// forward sweep: du_k = K_k dx_k + kff_k, dx_{k+1} = Phi dx_k + Gam du_k, dx_0 = 0.
+// Lane 4i+j carries dx of chain i and of chain j.
 __device__ void riccati_forward(const WarpCtx &w) {
     const SolveConsts &c = *w.c;
-    const int N = c.N, lane = w.lane;
+    const int N = c.N;
     double *s = w.s;
     const WarpLayout &L = w.L;
-    if (lane < 10)
-        s[L.dx + lane] = 0.0;
-    __syncwarp();
+    const int pl = w.lane & 15, ci = pl >> 2, cj = pl & 3;
+    const Chain fi = load_chain(c.Phi, c.Gam, ci), fj = load_chain(c.Phi, c.Gam, cj);
+    const int si0 = chain_state(ci, 0), si1 = chain_state(ci, 1), si2 = chain_state(ci, 2);
+    double xi[3] = {0, 0, 0}, xj[3] = {0, 0, 0};
+    if (w.lane < 10)
+        s[L.dx + w.lane] = 0.0;
     for (int k = 0; k < N; ++k) {
-        if (lane < 4) {
-            double a = s[L.kf + 4 * k + lane];
-            if (k > 0) {
-                const double *Kg = s + L.Kg + 40 * k + 10 * lane;
-                const double *dx = s + L.dx + 10 * k;
-#pragma unroll
-                for (int j = 0; j < 10; ++j)
-                    a += Kg[j] * dx[j];
-            }
-            s[L.du + 4 * k + lane] = a;
+        double part = 0.0;
+        if (k > 0) {
+            const double *Kg = s + L.Kg + 48 * k;
+            part = Kg[pl] * xj[0] + Kg[16 + pl] * xj[1] + Kg[32 + pl] * xj[2];
         }
-        __syncwarp();
-        if (lane < 10)
-            s[L.dx + 10 * (k + 1) + lane] = phi_row_dot(c.Phi, lane, s + L.dx + 10 * k) +
-                                            gam_row_dot(c.Gam, lane, s + L.du + 4 * k);
-        __syncwarp();
+        part += __shfl_xor_sync(AMPC_FULL_MASK, part, 1);
+        part += __shfl_xor_sync(AMPC_FULL_MASK, part, 2);
+        const double ui = s[L.kf + 4 * k + ci] + part;
+        const double uj = __shfl_sync(AMPC_FULL_MASK, ui, 4 * cj);
+        double yi[3], yj[3];
+        chain_F(fi, xi, ui, yi);
+        chain_F(fj, xj, uj, yj);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            xi[a] = yi[a];
+            xj[a] = yj[a];
+        }
+        if (w.lane < 16 && cj == 0) {
+            s[L.du + 4 * k + ci] = ui;
+            s[L.dx + 10 * (k + 1) + si0] = xi[0];
+            if (ci < 3) {
+                s[L.dx + 10 * (k + 1) + si1] = xi[1];
+                s[L.dx + 10 * (k + 1) + si2] = xi[2];
+            }
+        }
     }
+    __syncwarp();
 }
 
 struct SolveOut {
