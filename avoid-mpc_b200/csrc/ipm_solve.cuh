@@ -33,7 +33,7 @@ namespace ampc {
 
 // per-warp shared-memory layout, in doubles
 struct WarpLayout {
-    int x, u, zl, zu, dx, du, q, r, rt, rdiag, Hc, Kg, kf, cs, total;
+    int x, u, zl, zu, dx, du, dxt, dut, q, r, rt, rdiag, Hc, Kg, kf, cs, total;
     __host__ __device__ explicit WarpLayout(int N) {
         int o = 0;
         x = o, o += (N + 1) * 10;
@@ -42,6 +42,8 @@ struct WarpLayout {
         zu = o, o += N * 4;
         dx = o, o += (N + 1) * 10;
         du = o, o += N * 4;
+        dxt = o, o += (N + 1) * 10; // trial displacement of the line search
+        dut = o, o += N * 4;
         q = o, o += (N + 1) * 10;
         r = o, o += N * 4;
         rt = o, o += N * 4;
@@ -127,11 +129,11 @@ struct WarpCtx {
         : c(c_), s(s_), L(c_->N), prefix(p_), lane(lane_) {}
 };
 
-// Evaluate the objective at (x + alpha*dx, u + alpha*du) [trial] or at (x, u).
+// Evaluate the objective at the trial point (x + dxt, u + dut) or at (x, u).
 // lane = stage.  full: also writes q (grad x), r (grad u) and Hc (Hessian).
 // Returns the warp-wide objective value (identical in all lanes).
 template <bool FULL, bool TRIAL>
-__device__ double eval_cost(const WarpCtx &w, double alpha, double eps) {
+__device__ double eval_cost(const WarpCtx &w, double eps) {
     const SolveConsts &c = *w.c;
     const int N = c.N, K = c.K;
     double *s = w.s;
@@ -146,7 +148,7 @@ __device__ double eval_cost(const WarpCtx &w, double alpha, double eps) {
         for (int i = 0; i < 4; ++i) {
             double uu = s[L.u + 4 * kc + i];
             if (TRIAL)
-                uu += alpha * s[L.du + 4 * kc + i];
+                uu += s[L.dut + 4 * kc + i];
             const double d = uu - (i == 2 ? AMPC_GZ : 0.0);
             acc += qu[i] * d * d;
             if (FULL)
@@ -157,7 +159,7 @@ __device__ double eval_cost(const WarpCtx &w, double alpha, double eps) {
         for (int i = 0; i < 10; ++i) {
             x[i] = s[L.x + 10 * k + i];
             if (TRIAL)
-                x[i] += alpha * s[L.dx + 10 * k + i];
+                x[i] += s[L.dxt + 10 * k + i];
         }
         if (kc == N - 1) { // terminal (mpc_obstacle_casadi.py:168-170)
             const double *tg = w.prefix + 10 + 10 * N + 3 * K * N;
@@ -485,6 +487,33 @@ __device__ void riccati_forward(const WarpCtx &w) {
     __syncwarp();
 }
 
+// dxt = linear roll-out of dut (dxt_0 = 0, dxt_{k+1} = Phi dxt_k + Gam dut_k); lane i < 4 = chain i
+__device__ void rollout_delta(const WarpCtx &w) {
+    const SolveConsts &c = *w.c;
+    const int N = c.N;
+    double *s = w.s;
+    const WarpLayout &L = w.L;
+    const int ci = w.lane & 3;
+    const Chain fi = load_chain(c.Phi, c.Gam, ci);
+    const int si0 = chain_state(ci, 0), si1 = chain_state(ci, 1), si2 = chain_state(ci, 2);
+    double xi[3] = {0, 0, 0};
+    if (w.lane < 10)
+        s[L.dxt + w.lane] = 0.0;
+    for (int k = 0; k < N; ++k) {
+        double y[3];
+        chain_F(fi, xi, s[L.dut + 4 * k + ci], y);
+        xi[0] = y[0], xi[1] = y[1], xi[2] = y[2];
+        if (w.lane < 4) {
+            s[L.dxt + 10 * (k + 1) + si0] = xi[0];
+            if (ci < 3) {
+                s[L.dxt + 10 * (k + 1) + si1] = xi[1];
+                s[L.dxt + 10 * (k + 1) + si2] = xi[2];
+            }
+        }
+    }
+    __syncwarp();
+}
+
 struct SolveOut {
     double cost, kkt_dual, kkt_compl, mu;
     int32_t iters, status, n_reg, n_backtrack;
@@ -533,7 +562,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
     double e_dual = 0.0, e_compl = 0.0;
     for (iter = 0;; ++iter) {
         double eps = fmax(c.eps_min, c.eps_scale * mu);
-        double f = eval_cost<true, false>(w, 0.0, eps);
+        double f = eval_cost<true, false>(w, eps);
         // barrier quantities at the current mu
         double c_mu = 0.0, ec = 0.0;
         for (int e = lane; e < nu; e += 32) {
@@ -592,7 +621,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         }
         if (mu_changed) {
             eps = fmax(c.eps_min, c.eps_scale * mu);
-            f = eval_cost<true, false>(w, 0.0, eps);
+            f = eval_cost<true, false>(w, eps);
             for (int e = lane; e < nu; e += 32) {
                 const int i = e & 3;
                 const double sl = s[L.u + e] - c.lb[i], su = c.ub[i] - s[L.u + e];
@@ -626,7 +655,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         riccati_forward(w);
         const double tau_f = fmax(tau_min, 1.0 - mu);
         // fraction to the boundary (IPOPT eq. (15)), barrier value, slope
-        double a_pri = 1.0, a_du = 1.0, bar0 = 0.0, gdw = 0.0;
+        double a_du = 1.0, bar0 = 0.0;
         for (int e = lane; e < nu; e += 32) {
             const int i = e & 3;
             const double uu = s[L.u + e], du = s[L.du + e];
@@ -634,37 +663,42 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             const double zl = s[L.zl + e], zu = s[L.zu + e];
             const double dzl = mu / sl - zl - zl / sl * du;
             const double dzu = mu / su - zu + zu / su * du;
-            if (du < 0.0)
-                a_pri = fmin(a_pri, -tau_f * sl / du);
-            if (du > 0.0)
-                a_pri = fmin(a_pri, tau_f * su / du);
             if (dzl < 0.0)
                 a_du = fmin(a_du, -tau_f * zl / dzl);
             if (dzu < 0.0)
                 a_du = fmin(a_du, -tau_f * zu / dzu);
             bar0 += log(sl) + log(su);
-            gdw += s[L.rt + e] * du;
         }
-        for (int e = 10 + lane; e < 10 * (N + 1); e += 32)
-            gdw += s[L.q + e] * s[L.dx + e];
-        a_pri = warp_min(a_pri);
         a_du = warp_min(a_du);
         bar0 = warp_sum(bar0);
-        gdw = warp_sum(gdw);
         const double phi0 = f - mu * bar0;
-        // Armijo backtracking on the barrier objective
-        double alpha = a_pri;
+        // Projected Armijo line search on the barrier objective: the step is limited PER
+        // COMPONENT by the fraction-to-the-boundary rule (a control that would cross its
+        // bound stops at (1-tau)*slack from it) instead of scaling the whole step by the most
+        // restrictive component; the states follow by linearity.  Every bound that wants to
+        // become active is reached in one iteration.
+        double alpha = 1.0;
         bool accepted = false;
         for (int ls = 0; ls < 40; ++ls) {
-            double bar = 0.0;
+            double bar = 0.0, gdt = 0.0;
             for (int e = lane; e < nu; e += 32) {
                 const int i = e & 3;
-                const double ut = s[L.u + e] + alpha * s[L.du + e];
-                bar += log(ut - c.lb[i]) + log(c.ub[i] - ut);
+                const double uu = s[L.u + e];
+                const double sl = uu - c.lb[i], su = c.ub[i] - uu;
+                double d = alpha * s[L.du + e];
+                d = fmin(fmax(d, -tau_f * sl), tau_f * su);
+                s[L.dut + e] = d;
+                gdt += s[L.rt + e] * d;
+                bar += log(sl + d) + log(su - d);
             }
+            __syncwarp();
+            rollout_delta(w);
+            for (int e = 10 + lane; e < 10 * (N + 1); e += 32)
+                gdt += s[L.q + e] * s[L.dxt + e];
             bar = warp_sum(bar);
-            const double phit = eval_cost<false, true>(w, alpha, eps) - mu * bar;
-            if (phit <= phi0 + eta * alpha * gdw + 10.0 * 2.220446049250313e-16 * fabs(phi0)) {
+            gdt = warp_sum(gdt);
+            const double phit = eval_cost<false, true>(w, eps) - mu * bar;
+            if (phit <= phi0 + eta * gdt + 10.0 * 2.220446049250313e-16 * fabs(phi0)) {
                 accepted = true;
                 break;
             }
@@ -682,7 +716,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             double zl = s[L.zl + e], zu = s[L.zu + e];
             const double dzl = mu / sl0 - zl - zl / sl0 * du;
             const double dzu = mu / su0 - zu + zu / su0 * du;
-            const double un = u0 + alpha * du;
+            const double un = u0 + s[L.dut + e];
             const double sl = un - c.lb[i], su = c.ub[i] - un;
             zl += a_du * dzl;
             zu += a_du * dzu;
@@ -693,11 +727,11 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             s[L.zu + e] = zu;
         }
         for (int e = 10 + lane; e < 10 * (N + 1); e += 32)
-            s[L.x + e] += alpha * s[L.dx + e];
+            s[L.x + e] += s[L.dxt + e];
         __syncwarp();
     }
     // results: w = [X_0,U_0,...,X_N]; objective without smoothing
-    const double cost = eval_cost<false, false>(w, 0.0, 0.0);
+    const double cost = eval_cost<false, false>(w, 0.0);
     for (int e = lane; e < 10 * (N + 1); e += 32) {
         const int k = e / 10, i = e - 10 * k;
         w_inout[14 * k + i] = s[L.x + e];

@@ -327,6 +327,11 @@ typedef struct {
     double bound_frac; /* 1e-2 (IPOPT default bound_frac) */
     double eps_min;    /* floor of the |s| smoothing, m/s */
     double eps_scale;  /* eps = max(eps_min, eps_scale * mu) */
+    double tau_min;    /* fraction-to-the-boundary floor (IPOPT tau_min, 0.99) */
+    double kappa_eps;  /* barrier sub-problem tolerance factor (IPOPT barrier_tol_factor, 10) */
+    double kappa_mu;   /* linear mu decrease (IPOPT mu_linear_decrease_factor, 0.2) */
+    double theta_mu;   /* superlinear mu decrease (IPOPT mu_superlinear_decrease_power, 1.5) */
+    int32_t proj_step; /* 1: per-component (projected) step limiting in the line search */
 } nlp_oracle_opts;
 
 typedef struct {
@@ -348,6 +353,11 @@ void nlp_oracle_default_opts(nlp_oracle_opts *o) {
     o->bound_frac = 1e-2;
     o->eps_min = 1e-5;
     o->eps_scale = 1.0;
+    o->tau_min = 0.99;
+    o->kappa_eps = 10.0;
+    o->kappa_mu = 0.2;
+    o->theta_mu = 1.5;
+    o->proj_step = 1;
 }
 
 typedef struct {
@@ -544,7 +554,7 @@ int nlp_oracle_solve(int N, int K, double dt, const double *p, double *w, const 
     memcpy(s.lb, lbu, sizeof s.lb);
     memcpy(s.ub, ubu, sizeof s.ub);
     const size_t nxs = (size_t)(N + 1) * NX, nus = (size_t)N * NU;
-    double *buf = (double *)calloc(nxs * 4 + nus * 10 + (size_t)(N + 1) * NX * NX + nus * NX, sizeof(double));
+    double *buf = (double *)calloc(nxs * 5 + nus * 11 + (size_t)(N + 1) * NX * NX + nus * NX, sizeof(double));
     double *b = buf;
     s.x = b, b += nxs;
     s.q = b, b += nxs;
@@ -565,10 +575,14 @@ int nlp_oracle_solve(int N, int K, double dt, const double *p, double *w, const 
     b += nus;
     double *rdiag = b;
     b += nus;
+    double *dut = b;
+    b += nus;
+    double *dxt = b;
+    b += nxs;
     s.Q = b, b += (size_t)(N + 1) * NX * NX;
     s.Kg = b, b += nus * NX;
 
-    const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+    const double kappa_eps = opt->kappa_eps, kappa_mu = opt->kappa_mu, theta_mu = opt->theta_mu, tau_min = opt->tau_min;
     const double eta = 1e-4, kappa_sigma = 1e10;
     const double mu_min = opt->tol / 10.0;
 #define EPS_OF(m) fmax(opt->eps_min, opt->eps_scale * (m))
@@ -709,19 +723,54 @@ int nlp_oracle_solve(int N, int K, double dt, const double *p, double *w, const 
             gdw += s.q[i] * s.dx[i];
         for (size_t i = 0; i < nus; ++i)
             gdw += rt[i] * s.du[i];
-        double alpha = a_pri;
+        /* Projected line search: the step is limited PER COMPONENT by the
+         * fraction-to-the-boundary rule (a control that would cross its bound stops
+         * at distance (1-tau)*slack from it) instead of scaling the whole step by
+         * the most restrictive component; the states follow by linearity
+         * (dx_t = rollout of du_t).  Every bound that wants to become active is
+         * reached in one iteration.  The Armijo test uses the actual displacement. */
+        double alpha = opt->proj_step ? 1.0 : a_pri;
         int accepted = 0;
         for (int ls = 0; ls < 40; ++ls) {
-            for (size_t i = 0; i < nxs; ++i)
-                xt[i] = s.x[i] + alpha * s.dx[i];
-            double bar = 0;
+            double bar = 0, gdt = 0;
             for (size_t i = 0; i < nus; ++i) {
-                ut[i] = s.u[i] + alpha * s.du[i];
+                const double sl = s.u[i] - s.lb[i % NU], su = s.ub[i % NU] - s.u[i];
+                double d = alpha * s.du[i];
+                if (opt->proj_step) {
+                    if (d < -tau_f * sl)
+                        d = -tau_f * sl;
+                    if (d > tau_f * su)
+                        d = tau_f * su;
+                }
+                dut[i] = d;
+                ut[i] = s.u[i] + d;
+                gdt += rt[i] * d;
                 bar += log(ut[i] - s.lb[i % NU]) + log(s.ub[i % NU] - ut[i]);
+            }
+            if (opt->proj_step) { /* dx_t by linearity */
+                for (int i = 0; i < NX; ++i)
+                    dxt[i] = 0.0;
+                for (int k = 0; k < N; ++k)
+                    for (int i = 0; i < NX; ++i) {
+                        double a = 0;
+                        for (int j = 0; j < NX; ++j)
+                            a += s.Phi[i * NX + j] * dxt[NX * k + j];
+                        for (int j = 0; j < NU; ++j)
+                            a += s.Gam[i * NU + j] * dut[NU * k + j];
+                        dxt[NX * (k + 1) + i] = a;
+                    }
+                for (size_t i = 0; i < nxs; ++i) {
+                    xt[i] = s.x[i] + dxt[i];
+                    gdt += s.q[i] * dxt[i];
+                }
+            } else {
+                for (size_t i = 0; i < nxs; ++i)
+                    xt[i] = s.x[i] + alpha * s.dx[i];
+                gdt = alpha * gdw;
             }
             const double phit = eval_all(&s, xt, ut, 0, EPS_OF(mu)) - mu * bar;
             /* rounding-level slack so steps at the noise floor of phi are not rejected */
-            if (phit <= phi0 + eta * alpha * gdw + 10 * 2.220446049250313e-16 * fabs(phi0)) {
+            if (phit <= phi0 + eta * gdt + 10 * 2.220446049250313e-16 * fabs(phi0)) {
                 accepted = 1;
                 break;
             }

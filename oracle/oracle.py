@@ -37,7 +37,9 @@ def build(force: bool = False) -> None:
 class Opts(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int32), ("mu_init", C.c_double),
                 ("bound_push", C.c_double), ("bound_frac", C.c_double),
-                ("eps_min", C.c_double), ("eps_scale", C.c_double)]
+                ("eps_min", C.c_double), ("eps_scale", C.c_double), ("tau_min", C.c_double),
+                ("kappa_eps", C.c_double), ("kappa_mu", C.c_double), ("theta_mu", C.c_double),
+                ("proj_step", C.c_int32)]
 
 
 class Info(C.Structure):
