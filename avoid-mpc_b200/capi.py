@@ -23,7 +23,7 @@ SYMBOLS = [
     "ampc_api_version", "ampc_create", "ampc_destroy", "ampc_last_error",
     "ampc_set_weights", "ampc_set_tau", "ampc_set_gains", "ampc_set_radius", "ampc_set_accel_limits",
     "ampc_default_solver_opts", "ampc_set_solver_opts", "ampc_get_dynamics",
-    "ampc_cloud_set", "ampc_cloud_set_batch", "ampc_cloud_set_batch_dev", "ampc_cloud_index_dev", "ampc_cloud_count",
+    "ampc_cloud_set", "ampc_cloud_set_batch", "ampc_cloud_set_batch_dev", "ampc_cloud_index_dev", "ampc_cloud_set_layout", "ampc_cloud_count",
     "ampc_knn_batch", "ampc_knn_batch_dev", "ampc_solve_batch", "ampc_solve_batch_dev",
     "ampc_round_batch", "ampc_round_batch_dev", "ampc_last_prefix_dev",
     "ampc_best_of", "ampc_best_of_dev", "ampc_launch_count", "ampc_stream", "ampc_synchronize",
@@ -114,6 +114,7 @@ def lib():
         L.ampc_profile_enable.argtypes = [_vp, C.c_int]
         L.ampc_profile_get.argtypes = [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.ampc_cloud_index_dev.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]
+        L.ampc_cloud_set_layout.argtypes = [_vp, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -229,6 +230,9 @@ class Handle:
         cnt = np.full(S, Pn, dtype=np.int32) if counts is None else np.ascontiguousarray(counts, dtype=np.int32)
         self._ck(self.L.ampc_cloud_set_batch_dev(self.h, kind, first_scene, S, _ptr(xyz_dev), cnt.ctypes.data,
                                                  Pn * 16, stream))
+
+    def cloud_set_layout(self, row_width, kind=CLOUD_OBSTACLE):
+        self._ck(self.L.ampc_cloud_set_layout(self.h, kind, row_width))
 
     def cloud_count(self, scene, kind=CLOUD_OBSTACLE):
         n = C.c_int32()

@@ -59,9 +59,10 @@ struct ampc_handle {
     int n_w = 0, n_prefix = 0;
     cudaStream_t stream = nullptr;
     // clouds: [kind] slot buffers + counts
-    DevBuf cloud[2], counts[2], boxes[2];
+    DevBuf cloud[2], counts[2], boxes[2], nan_flags[2];
     int slot_points[2] = {0, 0};
     int slot_tiles[2] = {0, 0};
+    int row_w[2] = {0, 0}; // organised-cloud row pitch hint per kind (0: unorganised)
     DevBuf raw_stage; // staging for stride != 16 uploads
     // batch workspaces
     DevBuf queries, prefix, w, info, knn_idx, knn_d2, knn_cnt, knn_pts, scene_of, x0, ref, posx, replan;
@@ -293,7 +294,7 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     const int64_t warps = (int64_t)B * Q;
     const int target_warps = 148 * 16;
     if (warps < target_warps) {
-        const int max_useful = (h->slot_tiles[kind] + 63) / 64; // >= 64 tiles per segment
+        const int max_useful = (h->slot_points[kind] / KT_TILE + 63) / 64; // >= 64 tiles per segment
         segs = (int)((target_warps + warps - 1) / warps);
         if (segs > max_useful) segs = max_useful;
         if (segs > 64) segs = 64;
@@ -305,6 +306,7 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     P.counts = h->counts[kind].as<int32_t>();
     P.slot_points = h->slot_points[kind];
     P.slot_tiles = h->slot_tiles[kind];
+    P.row_w = h->row_w[kind];
     P.scene_of = scene_of_dev;
     P.queries = q_dev;
     P.Q = Q;
@@ -339,9 +341,19 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
     int slot;
     int rc = prof_begin(h, SEC_INDEX, st, &slot);
     if (rc) return rc;
-    cloud_index_kernel<<<n_scenes, KI_THREADS, 0, st>>>(h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(),
-                                                        h->counts[kind].as<int32_t>(), h->slot_points[kind],
-                                                        h->slot_tiles[kind], first_scene);
+    // enough CTAs to fill 148 SMs several times over, at least ~48 tiles per warp
+    int parts = (148 * 16 + n_scenes - 1) / n_scenes;
+    const int max_parts = (h->slot_points[kind] / KT_TILE) / ((KI_THREADS / 32) * 48) + 1;
+    if (parts > max_parts) parts = max_parts;
+    if (parts < 1) parts = 1;
+    cloud_index_kernel<<<dim3(parts, n_scenes), KI_THREADS, 0, st>>>(
+        h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
+        h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->row_w[kind], first_scene);
+    h->launches++;
+    CK(cudaGetLastError());
+    cloud_compact_kernel<<<n_scenes, KI_THREADS, 0, st>>>(
+        h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
+        h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->row_w[kind], first_scene);
     h->launches++;
     CK(cudaGetLastError());
     return prof_end(h, slot, st);
@@ -457,11 +469,15 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
             return bail(e, "cudaMalloc(clouds)");
         if ((e = h->counts[kind].reserve((size_t)cfg->max_scenes * 4)) != cudaSuccess)
             return bail(e, "cudaMalloc(counts)");
-        h->slot_tiles[kind] = (h->slot_points[kind] + KT_TILE - 1) / KT_TILE;
+        h->slot_tiles[kind] = (int)tile_capacity(h->slot_points[kind]);
         if ((e = h->boxes[kind].reserve((size_t)cfg->max_scenes * h->slot_tiles[kind] * 32)) != cudaSuccess)
             return bail(e, "cudaMalloc(tile boxes)");
         if ((e = cudaMemset(h->counts[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
             return bail(e, "cudaMemset(counts)");
+        if ((e = h->nan_flags[kind].reserve((size_t)cfg->max_scenes * 4)) != cudaSuccess)
+            return bail(e, "cudaMalloc(nan flags)");
+        if ((e = cudaMemset(h->nan_flags[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
+            return bail(e, "cudaMemset(nan flags)");
     }
     const size_t B = (size_t)cfg->max_batch, N = (size_t)cfg->N, K = (size_t)(cfg->K > 0 ? cfg->K : 1);
     struct { DevBuf *b; size_t n; } need[] = {
@@ -483,7 +499,7 @@ void ampc_destroy(ampc_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->raw_stage,
+    DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
                      &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost};
@@ -637,6 +653,16 @@ int ampc_cloud_set_batch_dev(ampc_handle *h, int32_t kind, int32_t first_scene, 
     return cloud_set_common(h, kind, first_scene, n_scenes, xyz_dev, true, counts_host,
                             scene_stride_bytes, 16, (cudaStream_t)stream);
 }
+int ampc_cloud_set_layout(ampc_handle *h, int32_t kind, int32_t row_width) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, kind);
+    if (rc) return rc;
+    if (row_width != 0 && row_width < 8)
+        return fail(h, AMPC_ERR_INVALID, "row_width must be 0 (unorganised) or >= 8");
+    h->row_w[kind] = row_width;
+    return AMPC_OK;
+}
+
 int ampc_cloud_count(ampc_handle *h, int32_t scene, int32_t kind, int32_t *n_out) {
     if (!h || !n_out) return AMPC_ERR_INVALID;
     int rc = check_kind(h, kind);

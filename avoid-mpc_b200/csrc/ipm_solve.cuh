@@ -299,11 +299,21 @@ __device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_
     const Chain fi = load_chain(c.Phi, c.Gam, ci), fj = load_chain(c.Phi, c.Gam, cj);
     const double *qg = c.wgt, *qp = c.wgt + 10;
     const int si0 = chain_state(ci, 0), si1 = chain_state(ci, 1), si2 = chain_state(ci, 2);
-    const bool diag = ci == cj, real = ci < 3 && cj < 3;
+    const bool diag = ci == cj, real = ci < 3 && cj < 3, yaw = pl == 15;
     const int lo = ci < cj ? ci : cj, hi = ci < cj ? cj : ci;
+    // branch-free access to this lane's entries of the stage Hessian: offsets into the
+    // compact store and 0/1 masks (constant over the sweep)
+    const double m_real = real ? 1.0 : 0.0, m_diag = diag ? 1.0 : 0.0;
+    const int o_pp = real ? sym3(lo, hi) : 0, o_pv = real ? 6 + ci * 3 + cj : 0;
+    const int o_vp = real ? 6 + cj * 3 + ci : 0, o_vv = real ? 15 + sym3(lo, hi) : 0;
+    const double q00c = yaw ? 2.0 * qp[3] + delta : (real && diag ? delta : 0.0);
+    const double q11c = real && diag ? delta : 0.0;
+    const double q22c = real && diag ? 2.0 * qp[si2] + delta : 0.0;
+    const int q1 = ci < 3 ? si1 : si0, q2 = ci < 3 ? si2 : si0; // padding reads a valid slot,
+    const double m_ax = ci < 3 ? 1.0 : 0.0;                     // masked to zero
     // terminal: P_N = diag(2 Q_goal) + delta, p_N = lam_N = q_N
     double P[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double pv[3] = {0, 0, 0}, lv[3];
+    double pv[3], lv[3];
     if (diag) {
         P[0] = 2.0 * qg[si0] + delta;
         if (ci < 3) {
@@ -312,22 +322,32 @@ __device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_
         }
     }
     pv[0] = s[L.q + 10 * N + si0];
-    if (ci < 3) {
-        pv[1] = s[L.q + 10 * N + si1];
-        pv[2] = s[L.q + 10 * N + si2];
-    }
+    pv[1] = m_ax * s[L.q + 10 * N + q1];
+    pv[2] = m_ax * s[L.q + 10 * N + q2];
     lv[0] = pv[0], lv[1] = pv[1], lv[2] = pv[2];
     double e_dual = 0.0;
     bool ok = true;
     for (int k = N - 1; k >= 0; --k) {
+        // operands from shared memory first (latency overlaps the products)
+        const double rdk = s[L.rdiag + 4 * k + ci], rtk = s[L.rt + 4 * k + ci];
+        const double guk = s[L.r + 4 * k + ci] - s[L.zl + 4 * k + ci] + s[L.zu + 4 * k + ci];
+        double Qb0 = q00c, Qb1 = 0.0, Qb3 = 0.0, Qb4 = q11c, qk0 = 0.0, qk1 = 0.0, qk2 = 0.0;
+        if (k > 0) {
+            const double *Hc = s + L.Hc + 21 * (k - 1);
+            Qb0 += m_real * Hc[o_pp];
+            Qb1 = m_real * Hc[o_pv];
+            Qb3 = m_real * Hc[o_vp];
+            Qb4 += m_real * Hc[o_vv];
+            qk0 = s[L.q + 10 * k + si0];
+            qk1 = m_ax * s[L.q + 10 * k + q1];
+            qk2 = m_ax * s[L.q + 10 * k + q2];
+        }
         // (1) products with this lane's block
         double t[3], bm[3], M[9], A[9];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
             t[a] = P[3 * a] * fj.g1 + P[3 * a + 1] * fj.g2 + P[3 * a + 2] * fj.g3;
-        double Sij = fi.g1 * t[0] + fi.g2 * t[1] + fi.g3 * t[2];
-        if (diag)
-            Sij += s[L.rdiag + 4 * k + ci] + delta;
+        const double Sij = fi.g1 * t[0] + fi.g2 * t[1] + fi.g3 * t[2] + m_diag * (rdk + delta);
         chain_FT(fi, t, bm);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
@@ -341,12 +361,10 @@ __device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_
             A[3 + b] = fi.c1 * M[b] + fi.d2 * M[3 + b];
             A[6 + b] = fi.c2 * M[b] + fi.c3 * M[3 + b] + fi.c4 * M[6 + b];
         }
-        const double bi = s[L.rt + 4 * k + ci] + fi.g1 * pv[0] + fi.g2 * pv[1] + fi.g3 * pv[2];
-        if (diag) {
-            const double gu = s[L.r + 4 * k + ci] + fi.g1 * lv[0] + fi.g2 * lv[1] + fi.g3 * lv[2];
-            e_dual = fmax(e_dual, fabs(gu - s[L.zl + 4 * k + ci] + s[L.zu + 4 * k + ci]));
-        }
-        // (2) S = L D L' (3x3 for the axes + the yaw scalar), every lane redundantly
+        const double bi = rtk + fi.g1 * pv[0] + fi.g2 * pv[1] + fi.g3 * pv[2];
+        const double gu = guk + fi.g1 * lv[0] + fi.g2 * lv[1] + fi.g3 * lv[2];
+        e_dual = fmax(e_dual, m_diag * fabs(gu));
+        // (2) S = L D L' (3x3 for the axes; yaw is a decoupled scalar), every lane redundantly
         const double S00 = __shfl_sync(AMPC_FULL_MASK, Sij, 0), S10 = __shfl_sync(AMPC_FULL_MASK, Sij, 4);
         const double S20 = __shfl_sync(AMPC_FULL_MASK, Sij, 8), S11 = __shfl_sync(AMPC_FULL_MASK, Sij, 5);
         const double S21 = __shfl_sync(AMPC_FULL_MASK, Sij, 9), S22 = __shfl_sync(AMPC_FULL_MASK, Sij, 10);
@@ -360,82 +378,74 @@ __device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_
             ok = false;
             break; // uniform: every lane computed the same pivots
         }
-        // feed-forward kff = -S^-1 b  (b_l lives in lanes 5l)
-        double kff[4];
+        // feed-forward kff = -S^-1 b  (b_l lives in lane 5l; the yaw entry stays in lane 15)
+        double kff0, kff1, kff2;
+        const double kff3 = -bi * i3; // meaningful in lane 15 only
         {
             const double b0 = -__shfl_sync(AMPC_FULL_MASK, bi, 0), b1 = -__shfl_sync(AMPC_FULL_MASK, bi, 5);
-            const double b2 = -__shfl_sync(AMPC_FULL_MASK, bi, 10), b3 = -__shfl_sync(AMPC_FULL_MASK, bi, 15);
+            const double b2 = -__shfl_sync(AMPC_FULL_MASK, bi, 10);
             const double w1 = b1 - l10 * b0, w2 = b2 - l20 * b0 - l21 * w1;
-            kff[2] = w2 * i2;
-            kff[1] = w1 * i1 - l21 * kff[2];
-            kff[0] = b0 * i0 - l10 * kff[1] - l20 * kff[2];
-            kff[3] = b3 * i3;
+            kff2 = w2 * i2;
+            kff1 = w1 * i1 - l21 * kff2;
+            kff0 = b0 * i0 - l10 * kff1 - l20 * kff2;
         }
-        if (w.lane < 4)
-            s[L.kf + 4 * k + w.lane] = w.lane == 0 ? kff[0] : (w.lane == 1 ? kff[1] : (w.lane == 2 ? kff[2] : kff[3]));
+        if (w.lane == 0) {
+            s[L.kf + 4 * k + 0] = kff0;
+            s[L.kf + 4 * k + 1] = kff1;
+            s[L.kf + 4 * k + 2] = kff2;
+        }
+        if (w.lane == 15)
+            s[L.kf + 4 * k + 3] = kff3;
         if (k == 0)
             break; // dx_0 = 0: no feedback gain and no P_0 needed
-        // (3) Y = S^-1 Bm^(j)'  (4 controls x 3 components of chain j) and Bm^(i)
-        double Y[4][3], Bi[3][4];
+        // (3) Y = S^-1 Bm^(j)' (axis controls x components of chain j) and Bm^(i).  All
+        // couplings between the yaw chain and the axes are exactly zero, so only the three
+        // axis controls are gathered; the yaw block uses its own values.
+        double Y[3][3], Bi[3][3];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
             const double r0 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 0);
             const double r1 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 1);
             const double r2 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 2);
-            const double r3 = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * cj + 3);
             const double w1 = r1 - l10 * r0, w2 = r2 - l20 * r0 - l21 * w1;
             Y[2][cc] = w2 * i2;
             Y[1][cc] = w1 * i1 - l21 * Y[2][cc];
             Y[0][cc] = r0 * i0 - l10 * Y[1][cc] - l20 * Y[2][cc];
-            Y[3][cc] = r3 * i3;
 #pragma unroll
-            for (int l = 0; l < 4; ++l)
+            for (int l = 0; l < 3; ++l)
                 Bi[cc][l] = __shfl_sync(AMPC_FULL_MASK, bm[cc], 4 * ci + l);
         }
-        // feedback gain of control i on chain j: K = -Y[i][.]
-        if (w.lane < 16) {
-            double *Kg = s + L.Kg + 48 * k;
-            const double y0 = ci == 0 ? Y[0][0] : (ci == 1 ? Y[1][0] : (ci == 2 ? Y[2][0] : Y[3][0]));
-            const double y1 = ci == 0 ? Y[0][1] : (ci == 1 ? Y[1][1] : (ci == 2 ? Y[2][1] : Y[3][1]));
-            const double y2 = ci == 0 ? Y[0][2] : (ci == 1 ? Y[1][2] : (ci == 2 ? Y[2][2] : Y[3][2]));
-            Kg[pl] = -y0;
-            Kg[16 + pl] = -y1;
-            Kg[32 + pl] = -y2;
+        // feedback gains K = -Y: Kg[k][chain j][control l][component], written by lanes (0, j);
+        // the yaw gain -bm[0]/S33 by lane 15
+        if (w.lane < 3) {
+            double *Kg = s + L.Kg + 48 * k + 12 * cj;
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc)
+                    Kg[3 * l + cc] = -Y[l][cc];
         }
+        if (w.lane == 15)
+            s[L.Kg + 48 * k + 36 + 9] = -bm[0] * i3; // the never-written slots stay zero (cleared at start)
         // (4) P^(ij) <- Q^(ij) + A - Bm^(i) Y ;  p^(i) <- q^(i) + F_i' p^(i) + Bm^(i) kff ;
         //     lam^(i) <- q^(i) + F_i' lam^(i)
-        const double *Hc = s + L.Hc + 21 * (k - 1);
-        double Qb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        if (real) {
-            Qb[0] = Hc[sym3(lo, hi)];
-            Qb[1] = Hc[6 + ci * 3 + cj];
-            Qb[3] = Hc[6 + cj * 3 + ci];
-            Qb[4] = Hc[15 + sym3(lo, hi)];
-            if (diag) {
-                Qb[8] = 2.0 * qp[si2];
-                Qb[0] += delta, Qb[4] += delta, Qb[8] += delta;
-            }
-        } else if (diag) { // yaw
-            Qb[0] = 2.0 * qp[3] + delta;
-        }
+        const double yy = yaw ? i3 : 0.0; // yaw block: - bm bm' / S33
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b)
-                P[3 * a + b] = Qb[3 * a + b] + A[3 * a + b] - (Bi[a][0] * Y[0][b] + Bi[a][1] * Y[1][b] +
-                                                               Bi[a][2] * Y[2][b] + Bi[a][3] * Y[3][b]);
-        double qk[3] = {s[L.q + 10 * k + si0], 0.0, 0.0};
-        if (ci < 3) {
-            qk[1] = s[L.q + 10 * k + si1];
-            qk[2] = s[L.q + 10 * k + si2];
-        }
+                P[3 * a + b] = A[3 * a + b] - (Bi[a][0] * Y[0][b] + Bi[a][1] * Y[1][b] + Bi[a][2] * Y[2][b]) -
+                               yy * bm[a] * bm[b];
+        P[0] += Qb0, P[1] += Qb1, P[3] += Qb3, P[4] += Qb4, P[8] += q22c;
         double fp[3], fl[3];
         chain_FT(fi, pv, fp);
         chain_FT(fi, lv, fl);
+        const double kq[3] = {qk0, qk1, qk2};
+        const double ky = yaw ? kff3 : 0.0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            pv[a] = qk[a] + fp[a] + Bi[a][0] * kff[0] + Bi[a][1] * kff[1] + Bi[a][2] * kff[2] + Bi[a][3] * kff[3];
-            lv[a] = qk[a] + fl[a];
+            pv[a] = kq[a] + fp[a] + Bi[a][0] * kff0 + Bi[a][1] * kff1 + Bi[a][2] * kff2 + ky * bm[a];
+            lv[a] = kq[a] + fl[a];
         }
     }
     __syncwarp();
@@ -459,9 +469,10 @@ __device__ void riccati_forward(const WarpCtx &w) {
         s[L.dx + w.lane] = 0.0;
     for (int k = 0; k < N; ++k) {
         double part = 0.0;
-        if (k > 0) {
-            const double *Kg = s + L.Kg + 48 * k;
-            part = Kg[pl] * xj[0] + Kg[16 + pl] * xj[1] + Kg[32 + pl] * xj[2];
+        if (k > 0) { // Kg[k][chain j][control i][component]; axis/yaw cross gains are zero
+            const double *Kg = s + L.Kg + 48 * k + 12 * cj + 3 * ci;
+            const double m = ((ci < 3) == (cj < 3)) ? 1.0 : 0.0;
+            part = m * (Kg[0] * xj[0] + Kg[1] * xj[1] + Kg[2] * xj[2]);
         }
         part += __shfl_xor_sync(AMPC_FULL_MASK, part, 1);
         part += __shfl_xor_sync(AMPC_FULL_MASK, part, 2);
@@ -543,6 +554,8 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         s[L.zu + e] = mu / (hi - uu);
         s[L.du + e] = 0.0;
     }
+    for (int e = lane; e < 48 * N; e += 32)
+        s[L.Kg + e] = 0.0;
     for (int k = lane; k < N; k += 32) {
         const double yaw = w.prefix[10 + 10 * k + 3];
         s[L.cs + 2 * k] = cos(yaw);

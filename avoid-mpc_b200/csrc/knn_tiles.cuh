@@ -32,11 +32,43 @@ constexpr int KNN_KMAX = 32;      // top-k list = one entry per lane
 constexpr int KS_WARPS = 4;       // queries (warps) per search CTA
 constexpr int KS_CHUNK = 1024;    // tile lower bounds kept in shared memory per warp
 constexpr int KS_PICKS = 3;       // best-first tile picks before the storage-order sweep
-constexpr int KI_THREADS = 256;   // index kernel: 8 warps = 8 tiles per CTA iteration
+constexpr int KI_THREADS = 128;   // index kernels: 4 warps per CTA
 
-struct TileBox { // 32 bytes
-    float lx, ly, lz, hx, hy, hz, pad0, pad1;
+// Tile geometry.  row_w == 0: tile t = 64 consecutive records.  row_w > 0 (organised cloud,
+// the row pitch of the depth image the cloud was back-projected from): tile t = an 8x8 patch
+// of the image = 8 runs of 8 consecutive records (128 B each), row pitch row_w records -- a
+// compact box in space.  Any set of 64 indices gives a VALID box; the hint only makes it tight.
+struct TileGeom {
+    int row_w, tiles_x, n_tiles;
+    __host__ __device__ TileGeom(int n, int row_w_) : row_w(row_w_) {
+        if (row_w > 0) {
+            const int rows = (n + row_w - 1) / row_w;
+            tiles_x = (row_w + 7) / 8;
+            n_tiles = ((rows + 7) / 8) * tiles_x;
+        } else {
+            tiles_x = 0;
+            n_tiles = (n + KT_TILE - 1) / KT_TILE;
+        }
+    }
+    // record index of slot s (0..63) of tile t, or -1 if the slot is empty
+    __host__ __device__ int point(int t, int s, int n) const {
+        int i;
+        if (row_w > 0) {
+            const int ty = t / tiles_x, tx = t - ty * tiles_x;
+            const int col = 8 * tx + (s & 7);
+            if (col >= row_w)
+                return -1;
+            i = (8 * ty + (s >> 3)) * row_w + col;
+        } else {
+            i = t * KT_TILE + s;
+        }
+        return i < n ? i : -1;
+    }
 };
+// upper bound of TileGeom(n, w).n_tiles over n <= max_points, any w >= 8
+__host__ __device__ inline int64_t tile_capacity(int64_t max_points) {
+    return 2 * ((max_points + KT_TILE - 1) / KT_TILE) + 64;
+}
 
 struct KnnParams {
     const float4 *clouds;    // slot s at clouds + s*slot_points
@@ -44,6 +76,7 @@ struct KnnParams {
     const int32_t *counts;   // points held in each slot (after the NaN filter)
     int64_t slot_points;
     int64_t slot_tiles;
+    int32_t row_w;           // 0: unorganised cloud; >0: row pitch for 8x8 patch tiles
     const int32_t *scene_of; // [B] or nullptr (identity)
     const double *queries;   // [B][Q][3]
     int32_t Q, k, segs;
@@ -111,87 +144,131 @@ __device__ __forceinline__ void tile_box_store(float4 *boxes, int64_t tile, floa
     const float hx = warp_fmax(fmaxf(fmaxf(x0, -big), fmaxf(x1, -big)));
     const float hy = warp_fmax(fmaxf(fmaxf(y0, -big), fmaxf(y1, -big)));
     const float hz = warp_fmax(fmaxf(fmaxf(z0, -big), fmaxf(z1, -big)));
+    // points of the tile with all three coordinates finite-or-inf (not NaN): a lower bound
+    // on how many points lie inside the box
+    const bool f0 = v0 && p0.x == p0.x && p0.y == p0.y && p0.z == p0.z;
+    const bool f1 = v1 && p1.x == p1.x && p1.y == p1.y && p1.z == p1.z;
+    const int cnt = __popc(__ballot_sync(AMPC_FULL_MASK, f0)) + __popc(__ballot_sync(AMPC_FULL_MASK, f1));
     if (lane == 0) {
         boxes[2 * tile] = make_float4(lx, ly, lz, hx);
-        boxes[2 * tile + 1] = make_float4(hy, hz, 0.f, 0.f);
+        boxes[2 * tile + 1] = make_float4(hy, hz, __int_as_float(cnt), 0.f);
     }
 }
 
-// Index build: one CTA per scene slot; 8 warps x 64 points per iteration.
-// In-place, order-preserving NaN-x removal + tile boxes of the surviving cloud.
+// Index build, common path: grid (parts, scenes); every warp streams its share of the
+// scene's tiles (two tiles in flight per warp), reduces each tile's box and raises the
+// scene's flag if it meets a record whose x is NaN.  No block-wide synchronisation.
 __global__ void __launch_bounds__(KI_THREADS)
-cloud_index_kernel(float4 *clouds, float4 *boxes, int32_t *counts, int64_t slot_points,
-                   int64_t slot_tiles, int first_scene) {
+cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes,
+                   const int32_t *__restrict__ counts, int32_t *__restrict__ nan_flags,
+                   int64_t slot_points, int64_t slot_tiles, int row_w, int first_scene) {
+    const int scene = first_scene + blockIdx.y;
+    const float4 *c = clouds + (int64_t)scene * slot_points;
+    float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
+    const int n = counts[scene];
+    const int lane = threadIdx.x & 31;
+    constexpr int NW = KI_THREADS / 32;
+    const int gw = blockIdx.x * NW + (threadIdx.x >> 5), stride = gridDim.x * NW;
+    const TileGeom g(n, row_w);
+    bool nan_seen = false;
+    // per-lane record offsets inside a tile (slots lane and lane+32)
+    const int r0 = lane >> 3, cc = lane & 7;
+    const int o0 = row_w > 0 ? r0 * row_w + cc : lane;
+    const int o1 = row_w > 0 ? o0 + 4 * row_w : lane + 32;
+    auto tile_base = [&](int t, bool &colok) {
+        if (row_w > 0) {
+            const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
+            colok = 8 * tx + cc < row_w;
+            return 8 * ty * row_w + 8 * tx;
+        }
+        colok = true;
+        return t * KT_TILE;
+    };
+    int t = gw;
+    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0; // tiles t and t+stride
+    bool va0 = false, va1 = false, vb0 = false, vb1 = false;
+    auto fetch = [&](int tt, float4 &p0, float4 &p1, bool &v0, bool &v1) {
+        v0 = v1 = false;
+        if (tt < g.n_tiles) {
+            bool colok;
+            const int base = tile_base(tt, colok);
+            v0 = colok && base + o0 < n;
+            v1 = colok && base + o1 < n;
+            if (v0) p0 = c[base + o0];
+            if (v1) p1 = c[base + o1];
+        }
+    };
+    fetch(t, a0, a1, va0, va1);
+    fetch(t + stride, b0, b1, vb0, vb1);
+    for (; t < g.n_tiles; t += stride) {
+        const float4 p0 = a0, p1 = a1;
+        const bool v0 = va0, v1 = va1;
+        a0 = b0, a1 = b1, va0 = vb0, va1 = vb1;
+        fetch(t + 2 * stride, b0, b1, vb0, vb1);
+        nan_seen |= (v0 && p0.x != p0.x) || (v1 && p1.x != p1.x);
+        tile_box_store(bx, t, p0, p1, v0, v1, lane);
+    }
+    if (__any_sync(AMPC_FULL_MASK, nan_seen) && lane == 0)
+        atomicOr(&nan_flags[scene], 1);
+}
+
+// Index build, rare path (one CTA per scene, returns at once unless the scene's flag is set):
+// in-place, order-preserving removal of the records whose x is NaN (kd_tree_two.h:99-101),
+// then the boxes are rebuilt over the compacted cloud.
+__global__ void __launch_bounds__(KI_THREADS)
+cloud_compact_kernel(float4 *clouds, float4 *boxes, int32_t *counts, int32_t *nan_flags,
+                     int64_t slot_points, int64_t slot_tiles, int row_w, int first_scene) {
     const int scene = first_scene + blockIdx.x;
+    if (nan_flags[scene] == 0)
+        return;
     float4 *c = clouds + (int64_t)scene * slot_points;
     float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
     const int n = counts[scene];
     __shared__ int sWarp[KI_THREADS / 32];
-    __shared__ int sBase, sDirty;
+    __shared__ int sBase;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int PER_IT = (KI_THREADS / 32) * KT_TILE;
-    if (tid == 0) {
+    constexpr int NW = KI_THREADS / 32;
+    constexpr int PER_IT = NW * KT_TILE;
+    if (tid == 0)
         sBase = 0;
-        sDirty = 0;
-    }
     __syncthreads();
-    // software prefetch of the next iteration's two records
-    float4 nx0 = make_float4(0, 0, 0, 0), nx1 = nx0;
-    {
-        const int i0 = warp * KT_TILE + lane, i1 = i0 + 32;
-        if (i0 < n) nx0 = c[i0];
-        if (i1 < n) nx1 = c[i1];
-    }
     for (int start = 0; start < n; start += PER_IT) {
         const int tb = start + warp * KT_TILE;
-        const int i0 = tb + lane, i1 = i0 + 32;
-        const float4 p0 = nx0, p1 = nx1;
-        {
-            const int j0 = i0 + PER_IT, j1 = i1 + PER_IT;
-            if (j0 < n) nx0 = c[j0];
-            if (j1 < n) nx1 = c[j1];
-        }
-        const bool in0 = i0 < n, in1 = i1 < n;
-        const bool k0 = in0 && !(p0.x != p0.x), k1 = in1 && !(p1.x != p1.x);
+        const int j0 = tb + lane, j1 = j0 + 32;
+        float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
+        if (j0 < n) p0 = c[j0];
+        if (j1 < n) p1 = c[j1];
+        const bool k0 = j0 < n && !(p0.x != p0.x), k1 = j1 < n && !(p1.x != p1.x);
         const unsigned m0 = __ballot_sync(AMPC_FULL_MASK, k0), m1 = __ballot_sync(AMPC_FULL_MASK, k1);
-        const int cw = __popc(m0) + __popc(m1);
-        const int nin = __popc(__ballot_sync(AMPC_FULL_MASK, in0)) + __popc(__ballot_sync(AMPC_FULL_MASK, in1));
         if (lane == 0)
-            sWarp[warp] = cw;
-        // counts visible; every load of this iteration is complete.  (The prefetch reads
-        // records at >= start + PER_IT, which no write of this iteration can reach.)
-        __syncthreads();
+            sWarp[warp] = __popc(m0) + __popc(m1);
+        __syncthreads(); // counts visible; every read of this chunk is complete
         int off = sBase, total = 0;
 #pragma unroll
-        for (int w = 0; w < KI_THREADS / 32; ++w) {
+        for (int w = 0; w < NW; ++w) {
             const int v = sWarp[w];
             if (w < warp) off += v;
             total += v;
         }
-        const bool shifted = (off != tb) || (cw != nin);
-        if (shifted) { // some NaN seen: compact (writes land at or below this iteration's reads)
-            const unsigned lt = (1u << lane) - 1u;
-            if (k0) c[off + __popc(m0 & lt)] = p0;
-            if (k1) c[off + __popc(m0) + __popc(m1 & lt)] = p1;
-            if (lane == 0 && tb < n) sDirty = 1;
-        } else if (tb < n) {
-            tile_box_store(bx, tb / KT_TILE, p0, p1, in0, in1, lane);
-        }
+        const unsigned lt = (1u << lane) - 1u;
+        if (k0) c[off + __popc(m0 & lt)] = p0; // lands at or below this chunk's reads
+        if (k1) c[off + __popc(m0) + __popc(m1 & lt)] = p1;
         __syncthreads();
         if (tid == 0) sBase += total;
         __syncthreads();
     }
     const int m = sBase;
-    if (tid == 0) counts[scene] = m;
-    if (sDirty) { // rare: rebuild every box from the compacted cloud
-        const int nt = (m + KT_TILE - 1) / KT_TILE;
-        for (int t = warp; t < nt; t += KI_THREADS / 32) {
-            const int i0 = t * KT_TILE + lane, i1 = i0 + 32;
-            float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
-            if (i0 < m) p0 = c[i0];
-            if (i1 < m) p1 = c[i1];
-            tile_box_store(bx, t, p0, p1, i0 < m, i1 < m, lane);
-        }
+    if (tid == 0) {
+        counts[scene] = m;
+        nan_flags[scene] = 0;
+    }
+    const TileGeom g(m, row_w);
+    for (int t = warp; t < g.n_tiles; t += NW) {
+        const int i0 = g.point(t, lane, m), i1 = g.point(t, lane + 32, m);
+        float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
+        if (i0 >= 0) p0 = c[i0];
+        if (i1 >= 0) p1 = c[i1];
+        tile_box_store(bx, t, p0, p1, i0 >= 0, i1 >= 0, lane);
     }
 }
 
@@ -215,27 +292,27 @@ __device__ __forceinline__ void topk_insert(TopK &e, int k, double d, uint32_t i
 }
 
 // scan one tile: exact distances of its (up to) 64 points, candidates into the list
-__device__ __forceinline__ void scan_tile(const float4 *cloud, int n, int tile, double qx, double qy,
-                                          double qz, TopK &e, double &kth, int k, int lane) {
-    const int base = tile * KT_TILE;
-    const int i0 = base + lane, i1 = i0 + 32;
+__device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const TileGeom &g, int tile,
+                                          double qx, double qy, double qz, TopK &e, double &kth, int k,
+                                          int lane) {
+    const int i0 = g.point(tile, lane, n), i1 = g.point(tile, lane + 32, n);
     double d0 = INFINITY, d1 = INFINITY;
-    if (i0 < n) {
+    if (i0 >= 0) {
         const float4 p = knn_ldg(cloud + i0);
         d0 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
     }
-    if (i1 < n) {
+    if (i1 >= 0) {
         const float4 p = knn_ldg(cloud + i1);
         d1 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
     }
-    unsigned m0 = __ballot_sync(AMPC_FULL_MASK, i0 < n && d0 <= kth);
-    unsigned m1 = __ballot_sync(AMPC_FULL_MASK, i1 < n && d1 <= kth);
+    unsigned m0 = __ballot_sync(AMPC_FULL_MASK, i0 >= 0 && d0 <= kth);
+    unsigned m1 = __ballot_sync(AMPC_FULL_MASK, i1 >= 0 && d1 <= kth);
     while (m0) {
         const int src = __ffs(m0) - 1;
         m0 &= m0 - 1;
         const double d = __shfl_sync(AMPC_FULL_MASK, d0, src);
         if (d <= kth) {
-            topk_insert(e, k, d, (uint32_t)(base + src), lane);
+            topk_insert(e, k, d, (uint32_t)__shfl_sync(AMPC_FULL_MASK, i0, src), lane);
             kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
         }
     }
@@ -244,7 +321,7 @@ __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, int tile, 
         m1 &= m1 - 1;
         const double d = __shfl_sync(AMPC_FULL_MASK, d1, src);
         if (d <= kth) {
-            topk_insert(e, k, d, (uint32_t)(base + 32 + src), lane);
+            topk_insert(e, k, d, (uint32_t)__shfl_sync(AMPC_FULL_MASK, i1, src), lane);
             kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
         }
     }
@@ -304,16 +381,16 @@ knn_search_kernel(const KnnParams P) {
     const float4 *boxes = P.boxes + (int64_t)scene * P.slot_tiles * 2;
     const double *qp = P.queries + ((int64_t)b * P.Q + q) * 3;
     const double qx = qp[0], qy = qp[1], qz = qp[2];
-    const int n_tiles = (n + KT_TILE - 1) / KT_TILE;
-    const int n_full = n / KT_TILE; // tiles 0..n_full-1 hold 64 >= k points
+    const TileGeom g(n, P.row_w);
+    const int n_tiles = g.n_tiles;
     const int per = (n_tiles + P.segs - 1) / P.segs;
     const int t_begin = seg * per, t_end = min(n_tiles, t_begin + per);
     double *lbuf = sLB[warp];
     unsigned short *cand = sCand[warp];
     TopK e{INFINITY, 0xffffffffu};
     // `bound`: no point farther than this can be among the k nearest.  It is the min of
-    // the list's k-th entry and of the farthest-corner distance of any full tile seen
-    // (such a tile alone already holds 64 >= k points within that distance).
+    // the list's k-th entry and of the farthest-corner distance of any tile seen that holds
+    // at least k points (that tile alone already has k points within that distance).
     double bound = INFINITY;
 
     for (int c0 = t_begin; c0 < t_end; c0 += KS_CHUNK) {
@@ -323,7 +400,7 @@ knn_search_kernel(const KnnParams P) {
             const float4 a = knn_ldg(boxes + 2 * (int64_t)(c0 + j));
             const float4 h = knn_ldg(boxes + 2 * (int64_t)(c0 + j) + 1);
             lbuf[j] = knn_box_lb(qx, qy, qz, a.x, a.y, a.z, a.w, h.x, h.y);
-            if (c0 + j < n_full)
+            if (__float_as_int(h.z) >= k) // the tile alone holds >= k points within its farthest corner
                 ubmin = fmin(ubmin, knn_box_ub(qx, qy, qz, a.x, a.y, a.z, a.w, h.x, h.y));
         }
         bound = fmin(bound, warp_min(ubmin));
@@ -362,7 +439,7 @@ knn_search_kernel(const KnnParams P) {
                 break;
             const int j = cand[best_c];
             double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
-            scan_tile(cloud, n, c0 + j, qx, qy, qz, e, kth, k, lane);
+            scan_tile(cloud, n, g, c0 + j, qx, qy, qz, e, kth, k, lane);
             bound = fmin(bound, kth);
             if (lane == 0)
                 lbuf[j] = NAN;
@@ -380,7 +457,7 @@ knn_search_kernel(const KnnParams P) {
                 if (lbj <= bound) { // the bound may have tightened since the ballot
                     const int jj = __shfl_sync(AMPC_FULL_MASK, j, src);
                     double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
-                    scan_tile(cloud, n, c0 + jj, qx, qy, qz, e, kth, k, lane);
+                    scan_tile(cloud, n, g, c0 + jj, qx, qy, qz, e, kth, k, lane);
                     bound = fmin(bound, kth);
                 }
             }

@@ -165,6 +165,8 @@ def run_ours(args):
     w0_np = np.stack([S.warm_start(args.warm, x0_np[b], ref_np[b], N_H) for b in range(B)])
     h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=npts, device=local)
     h.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+    if not args.unorganised:  # the clouds are row-major depth images: tell the index the row pitch
+        h.cloud_set_layout(S.image_shape(npts)[0])
     stream = torch.cuda.current_stream().cuda_stream
     h.cloud_set_batch_dev(clouds, stream=stream)
     x0 = torch.tensor(x0_np, device=dev)
@@ -360,6 +362,7 @@ def main():
     ap.add_argument("--tol", type=float, default=1e-8)
     ap.add_argument("--max-iter", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unorganised", action="store_true", help="do not pass the image row pitch to the index")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

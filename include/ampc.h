@@ -123,6 +123,12 @@ int ampc_cloud_set_batch(ampc_handle *h, int32_t kind, int32_t first_scene, int3
 int ampc_cloud_set_batch_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
                              const void *xyz_dev, const int32_t *counts_host,
                              int64_t scene_stride_bytes, void *stream);
+/* Optional layout hint for the clouds of `kind`: the cloud is an ORGANISED cloud stored
+ * row-major with `row_width` records per image row (the resized depth image of
+ * FrameKDMap::ProcessDepth, src/FrameKDMap.cpp:106-125), so the index can use 8x8 image
+ * patches as tiles.  0 (default) = unorganised.  Only pruning efficiency depends on it,
+ * never the results.  Takes effect at the next cloud_set / cloud_index call. */
+int ampc_cloud_set_layout(ampc_handle *h, int32_t kind, int32_t row_width);
 /* rebuild the index (NaN filter + tile boxes) of clouds already resident in the
  * handle's slots, e.g. after writing a new depth frame's points in place; async */
 int ampc_cloud_index_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,

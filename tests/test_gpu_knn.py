@@ -113,3 +113,19 @@ def test_knn_single_instance_uses_segments_and_large_cloud():
     # size-independent property: results are sorted and are true distances of the indices
     assert (np.diff(d2[0], axis=1) >= 0).all()
     h.close()
+
+
+@pytest.mark.parametrize("row_w", [0, 125, 64, 9, 1000])
+def test_layout_hint_changes_nothing_but_speed(row_w):
+    """8x8 image-patch tiles (organised-cloud hint) vs linear tiles: identical results, also with
+    NaN records (which shift the grid) and a width that does not divide the cloud."""
+    npts, Q, k = 10000, 20, 16
+    h = A.Handle(N=Q, K=k, max_batch=3, max_points=npts)
+    h.cloud_set_layout(row_w)
+    clouds = [S.forest_cloud(40, npts)[0], S.forest_cloud(41, 9973)[0], S.forest_cloud(42, npts)[0].copy()]
+    clouds[2][5::97, 0] = np.nan
+    for s, c in enumerate(clouds):
+        h.cloud_set(s, c)
+    queries = np.stack([S.states(40 + s, Q)[1][:, :3] for s in range(3)])
+    _check(h, clouds, queries, k)
+    h.close()
