@@ -72,6 +72,7 @@ struct ampc_handle {
     std::string err;
     int solve_smem_set = 0;
     int knn_smem_set = 0;
+    bool index_smem_set = false;
     // optional per-kernel timing of ampc_round_batch_dev (CUDA events on the caller's stream)
     bool prof = false;
     std::vector<cudaEvent_t> prof_ev; // pairs (start, stop), tagged with a section
@@ -341,12 +342,15 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
     int slot;
     int rc = prof_begin(h, SEC_INDEX, st, &slot);
     if (rc) return rc;
-    // enough CTAs to fill 148 SMs several times over, at least ~48 tiles per warp
-    int parts = (148 * 16 + n_scenes - 1) / n_scenes;
-    const int max_parts = (h->slot_points[kind] / KT_TILE) / ((KI_THREADS / 32) * 48) + 1;
-    if (parts > max_parts) parts = max_parts;
+    // ~6 bands (6 x 32 KB) per CTA, so that the double buffer has something to overlap
+    const int64_t max_bands = (h->slot_points[kind] + 8 * KI_COLS - 1) / (8 * KI_COLS) + 8;
+    int parts = (int)((max_bands + 5) / 6);
     if (parts < 1) parts = 1;
-    cloud_index_kernel<<<dim3(parts, n_scenes), KI_THREADS, 0, st>>>(
+    if (!h->index_smem_set) {
+        CK(cudaFuncSetAttribute(cloud_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KI_BAND_BYTES));
+        h->index_smem_set = true;
+    }
+    cloud_index_kernel<<<dim3(parts, n_scenes), KI_THREADS, 2 * KI_BAND_BYTES, st>>>(
         h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
         h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->row_w[kind], first_scene);
     h->launches++;

@@ -117,37 +117,39 @@ __device__ __forceinline__ float4 knn_ldg(const float4 *p) {
     return __ldg(p); // ld.global.nc.v4
 }
 
-// ---- order-preserving float <-> uint map so that redux.sync (integer warp
-// reduction, one instruction) yields exact float min / max
-__device__ __forceinline__ unsigned f2ord(float f) {
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+// ---- order-preserving float <-> int map (flip the magnitude bits of negative values) so
+// that redux.sync (integer warp reduction, one instruction) yields exact float min / max
+__device__ __forceinline__ int f2ord(float f) {
+    const int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
 }
-__device__ __forceinline__ float ord2f(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+__device__ __forceinline__ float ord2f(int i) {
+    return __int_as_float(i ^ ((i >> 31) & 0x7fffffff));
 }
-__device__ __forceinline__ float warp_fmin(float v) {
-    return ord2f(__reduce_min_sync(AMPC_FULL_MASK, f2ord(fminf(v, INFINITY)))); // NaN -> +inf
+__device__ __forceinline__ float warp_fmin(float v) { // v must not be NaN
+    return ord2f(__reduce_min_sync(AMPC_FULL_MASK, f2ord(v)));
 }
 __device__ __forceinline__ float warp_fmax(float v) {
-    return ord2f(__reduce_max_sync(AMPC_FULL_MASK, f2ord(fmaxf(v, -INFINITY)))); // NaN -> -inf
+    return ord2f(__reduce_max_sync(AMPC_FULL_MASK, f2ord(v)));
 }
 
 __device__ __forceinline__ void tile_box_store(float4 *boxes, int64_t tile, float4 p0, float4 p1,
                                                bool v0, bool v1, int lane) {
+    // empty slots and NaN coordinates drop out: fminf/fmaxf return the non-NaN operand
     const float big = INFINITY;
     const float x0 = v0 ? p0.x : NAN, y0 = v0 ? p0.y : NAN, z0 = v0 ? p0.z : NAN;
     const float x1 = v1 ? p1.x : NAN, y1 = v1 ? p1.y : NAN, z1 = v1 ? p1.z : NAN;
-    const float lx = warp_fmin(fminf(fminf(x0, big), fminf(x1, big)));
-    const float ly = warp_fmin(fminf(fminf(y0, big), fminf(y1, big)));
-    const float lz = warp_fmin(fminf(fminf(z0, big), fminf(z1, big)));
-    const float hx = warp_fmax(fmaxf(fmaxf(x0, -big), fmaxf(x1, -big)));
-    const float hy = warp_fmax(fmaxf(fmaxf(y0, -big), fmaxf(y1, -big)));
-    const float hz = warp_fmax(fmaxf(fmaxf(z0, -big), fmaxf(z1, -big)));
-    // points of the tile with all three coordinates finite-or-inf (not NaN): a lower bound
-    // on how many points lie inside the box
-    const bool f0 = v0 && p0.x == p0.x && p0.y == p0.y && p0.z == p0.z;
-    const bool f1 = v1 && p1.x == p1.x && p1.y == p1.y && p1.z == p1.z;
+    const float lx = warp_fmin(fminf(fminf(x0, x1), big));
+    const float ly = warp_fmin(fminf(fminf(y0, y1), big));
+    const float lz = warp_fmin(fminf(fminf(z0, z1), big));
+    const float hx = warp_fmax(fmaxf(fmaxf(x0, x1), -big));
+    const float hy = warp_fmax(fmaxf(fmaxf(y0, y1), -big));
+    const float hz = warp_fmax(fmaxf(fmaxf(z0, z1), -big));
+    // points of the tile with no NaN coordinate: how many points certainly lie inside the box
+    // (x+y+z is NaN iff the slot is empty or some coordinate is NaN -- or inf-inf, which only
+    // under-counts, and an under-count is safe)
+    const float s0 = x0 + y0 + z0, s1 = x1 + y1 + z1;
+    const bool f0 = s0 == s0, f1 = s1 == s1;
     const int cnt = __popc(__ballot_sync(AMPC_FULL_MASK, f0)) + __popc(__ballot_sync(AMPC_FULL_MASK, f1));
     if (lane == 0) {
         boxes[2 * tile] = make_float4(lx, ly, lz, hx);
@@ -155,58 +157,144 @@ __device__ __forceinline__ void tile_box_store(float4 *boxes, int64_t tile, floa
     }
 }
 
-// Index build, common path: grid (parts, scenes); every warp streams its share of the
-// scene's tiles (two tiles in flight per warp), reduces each tile's box and raises the
-// scene's flag if it meets a record whose x is NaN.  No block-wide synchronisation.
+// ---- TMA bulk copy (cp.async.bulk, global -> shared, completion on an mbarrier) ----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// Index build, common path.  Grid (parts, scenes).  A CTA walks a range of "bands" of its
+// scene.  A band is what 32 tiles cover: 8 image rows x up to 256 columns for an organised
+// cloud (8 contiguous row segments), or 2048 consecutive records.  Each band is brought
+// into shared memory by TMA bulk copies (one per row segment, double buffered: the next
+// band streams in while the boxes of the current one are reduced), so HBM sees long
+// linear reads whatever the tile geometry.  Warps then reduce the tiles' boxes from shared
+// memory.  A record whose x is NaN raises the scene's flag (handled by cloud_compact_kernel).
+constexpr int KI_COLS = 256;                   // columns (records per row segment) per band
+constexpr int KI_BAND_BYTES = 8 * KI_COLS * 16; // 32 KB per buffer
 __global__ void __launch_bounds__(KI_THREADS)
 cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes,
                    const int32_t *__restrict__ counts, int32_t *__restrict__ nan_flags,
                    int64_t slot_points, int64_t slot_tiles, int row_w, int first_scene) {
+    extern __shared__ __align__(128) unsigned char ki_smem[];
+    __shared__ __align__(8) unsigned long long bar[2];
+    float4 *buf[2] = {reinterpret_cast<float4 *>(ki_smem), reinterpret_cast<float4 *>(ki_smem + KI_BAND_BYTES)};
     const int scene = first_scene + blockIdx.y;
     const float4 *c = clouds + (int64_t)scene * slot_points;
     float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
     const int n = counts[scene];
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = KI_THREADS / 32;
-    const int gw = blockIdx.x * NW + (threadIdx.x >> 5), stride = gridDim.x * NW;
     const TileGeom g(n, row_w);
+    // band grid of this scene
+    const int segs_x = row_w > 0 ? (row_w + KI_COLS - 1) / KI_COLS : 1;
+    const int bands_y = row_w > 0 ? (((n + row_w - 1) / row_w) + 7) / 8 : (n + 8 * KI_COLS - 1) / (8 * KI_COLS);
+    const int n_bands = bands_y * segs_x;
+    const int per = (n_bands + gridDim.x - 1) / gridDim.x;
+    const int b_begin = blockIdx.x * per, b_end = min(n_bands, b_begin + per);
+    if (b_begin >= b_end)
+        return;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // geometry of band b: rows [8*by, 8*by+8), columns [c0, c0+cols); record index of (r, col)
+    auto issue = [&](int b, int which) { // one thread
+        const int by = b / segs_x, bxs = b - by * segs_x;
+        uint32_t total = 0;
+        if (row_w > 0 && row_w <= KI_COLS) { // the 8 rows of the band are one contiguous span
+            const int64_t start = (int64_t)8 * by * row_w;
+            total = (uint32_t)min((int64_t)8 * row_w, (int64_t)n - start) * 16u;
+            mbar_expect_tx(&bar[which], total);
+            bulk_g2s(buf[which], c + start, total, &bar[which]);
+        } else if (row_w > 0) {
+            const int c0 = bxs * KI_COLS, cols = min(KI_COLS, row_w - c0);
+            uint32_t bytes[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int64_t start = (int64_t)(8 * by + r) * row_w + c0;
+                const int64_t cnt = min((int64_t)cols, (int64_t)n - start);
+                bytes[r] = cnt > 0 ? (uint32_t)cnt * 16u : 0u;
+                total += bytes[r];
+            }
+            mbar_expect_tx(&bar[which], total);
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (bytes[r])
+                    bulk_g2s(buf[which] + r * KI_COLS, c + (int64_t)(8 * by + r) * row_w + c0, bytes[r], &bar[which]);
+        } else {
+            const int64_t start = (int64_t)b * 8 * KI_COLS;
+            total = (uint32_t)min((int64_t)8 * KI_COLS, (int64_t)n - start) * 16u;
+            mbar_expect_tx(&bar[which], total);
+            bulk_g2s(buf[which], c + start, total, &bar[which]);
+        }
+    };
     bool nan_seen = false;
-    // per-lane record offsets inside a tile (slots lane and lane+32)
-    const int r0 = lane >> 3, cc = lane & 7;
-    const int o0 = row_w > 0 ? r0 * row_w + cc : lane;
-    const int o1 = row_w > 0 ? o0 + 4 * row_w : lane + 32;
-    auto tile_base = [&](int t, bool &colok) {
+    if (tid == 0)
+        issue(b_begin, 0);
+    for (int b = b_begin; b < b_end; ++b) {
+        const int it = b - b_begin, cur = it & 1;
+        if (tid == 0 && b + 1 < b_end)
+            issue(b + 1, cur ^ 1); // buffer cur^1 was released by the barrier ending iteration it-1
+        mbar_wait(&bar[cur], (it >> 1) & 1);
+        const float4 *sb = buf[cur];
+        const int by = b / segs_x, bxs = b - by * segs_x;
         if (row_w > 0) {
-            const int ty = t / g.tiles_x, tx = t - ty * g.tiles_x;
-            colok = 8 * tx + cc < row_w;
-            return 8 * ty * row_w + 8 * tx;
+            const int c0 = bxs * KI_COLS, cols = min(KI_COLS, row_w - c0);
+            const int tiles_here = (cols + 7) / 8;
+            const int r0 = lane >> 3, cc = lane & 7;
+            const int pitch = row_w <= KI_COLS ? row_w : KI_COLS; // records between rows in shared memory
+            for (int j = warp; j < tiles_here; j += NW) {
+                const int col = 8 * j + cc;
+                const int64_t i0 = (int64_t)(8 * by + r0) * row_w + c0 + col, i1 = i0 + 4 * (int64_t)row_w;
+                const bool v0 = col < cols && i0 < n, v1 = col < cols && i1 < n;
+                float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
+                if (v0) p0 = sb[r0 * pitch + col];
+                if (v1) p1 = sb[(r0 + 4) * pitch + col];
+                nan_seen |= (v0 && p0.x != p0.x) || (v1 && p1.x != p1.x);
+                tile_box_store(bx, (int64_t)by * g.tiles_x + c0 / 8 + j, p0, p1, v0, v1, lane);
+            }
+        } else {
+            const int64_t start = (int64_t)b * 8 * KI_COLS;
+            const int cnt = (int)min((int64_t)8 * KI_COLS, (int64_t)n - start);
+            const int tiles_here = (cnt + KT_TILE - 1) / KT_TILE;
+            for (int j = warp; j < tiles_here; j += NW) {
+                const int s0 = j * KT_TILE + lane, s1 = s0 + 32;
+                const bool v0 = s0 < cnt, v1 = s1 < cnt;
+                float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
+                if (v0) p0 = sb[s0];
+                if (v1) p1 = sb[s1];
+                nan_seen |= (v0 && p0.x != p0.x) || (v1 && p1.x != p1.x);
+                tile_box_store(bx, start / KT_TILE + j, p0, p1, v0, v1, lane);
+            }
         }
-        colok = true;
-        return t * KT_TILE;
-    };
-    int t = gw;
-    float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0; // tiles t and t+stride
-    bool va0 = false, va1 = false, vb0 = false, vb1 = false;
-    auto fetch = [&](int tt, float4 &p0, float4 &p1, bool &v0, bool &v1) {
-        v0 = v1 = false;
-        if (tt < g.n_tiles) {
-            bool colok;
-            const int base = tile_base(tt, colok);
-            v0 = colok && base + o0 < n;
-            v1 = colok && base + o1 < n;
-            if (v0) p0 = c[base + o0];
-            if (v1) p1 = c[base + o1];
-        }
-    };
-    fetch(t, a0, a1, va0, va1);
-    fetch(t + stride, b0, b1, vb0, vb1);
-    for (; t < g.n_tiles; t += stride) {
-        const float4 p0 = a0, p1 = a1;
-        const bool v0 = va0, v1 = va1;
-        a0 = b0, a1 = b1, va0 = vb0, va1 = vb1;
-        fetch(t + 2 * stride, b0, b1, vb0, vb1);
-        nan_seen |= (v0 && p0.x != p0.x) || (v1 && p1.x != p1.x);
-        tile_box_store(bx, t, p0, p1, v0, v1, lane);
+        __syncthreads(); // everyone is done with buf[cur]: it may be refilled
     }
     if (__any_sync(AMPC_FULL_MASK, nan_seen) && lane == 0)
         atomicOr(&nan_flags[scene], 1);
