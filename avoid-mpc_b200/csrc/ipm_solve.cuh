@@ -214,14 +214,24 @@ __device__ double eval_cost(const WarpCtx &w, double eps) {
         }
         // collision terms (mpc_obstacle_casadi.py:186-204)
         const double *ob = w.prefix + 10 + 10 * N + 3 * K * kc;
+        const double far2 = (c.radius + 1.25) * (c.radius + 1.25);
         for (int j = 0; j < K; ++j) {
             const double d0 = ob[3 * j] - x[0], d1 = ob[3 * j + 1] - x[1], d2 = ob[3 * j + 2] - x[2];
-            const double rr = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+            // softplus argument below -40 (clearance > 1.25 m): exp < 4.3e-18, so the term is
+            // < 1e-16*|v.n| in value and < 3e-15 in any derivative -- below the rounding of the
+            // sums it would be added to (this also covers the (1e4,1e4,1e4) padding points)
+            if (r2 > far2)
+                continue;
+            const double rr = sqrt(r2);
             const double ir = 1.0 / rr;
             const double n0 = d0 * ir, n1 = d1 * ir, n2 = d2 * ir;
             const double sv = x[4] * n0 + x[5] * n1 + x[6] * n2;
             const double e = exp((rr - c.radius) * -32.0);
-            const double sp = log(1.0 + e);
+            // log(1+e) and e/(1+e) equal e to within e^2 < 6e-17 when e < 2^-27: same accuracy
+            // as the reference's un-stabilised log(1+exp(x)), whose 1+e rounds at 1.1e-16
+            const bool tiny = e < 7.450580596923828e-09;
+            const double sp = tiny ? e : log(1.0 + e);
             const double hyp = sqrt(sv * sv + eps * eps);
             const double psi = hyp - eps;
             acc += lam * sp * psi;
@@ -229,7 +239,7 @@ __device__ double eval_cost(const WarpCtx &w, double eps) {
                 const double ih = 1.0 / hyp;
                 const double dpsi = sv * ih;
                 const double ddpsi = eps * eps * ih * ih * ih;
-                const double sig = e / (1.0 + e);
+                const double sig = tiny ? e : e / (1.0 + e);
                 const double w0 = (x[4] - sv * n0) * ir, w1 = (x[5] - sv * n1) * ir,
                              w2 = (x[6] - sv * n2) * ir;
                 const double nn[3] = {n0, n1, n2}, ww[3] = {w0, w1, w2};
