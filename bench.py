@@ -83,7 +83,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n = max(threads * 16, 128)
+    n = max(threads * 32, 256)
     rates, kind, desc = cpu_reference(n, args.npts, threads, steps=args.warmup + args.steps)
     rates = rates[args.warmup:]
     v = statistics.mean(rates)
@@ -273,13 +273,23 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     b_knn = 12 * npts + N_H * (24 + K_NB * 12)
+    traffic = None  # dram bytes per launch of the index kernel, from the committed ncu --set full capture
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))["cloud_index"]["metrics"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(m[k]["value"]) * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        pass
     index_ms_avg = index_ms / max(rounds, 1)
     knn_ms_avg = knn_ms / max(rounds, 1)
     stage_ms = index_ms_avg + knn_ms_avg
     achieved = B * b_knn / (index_ms_avg * 1e-3) / 1e9
     denom = total_ms if world == 1 else sum(step_ms)
     roofline = {"kernel": "cloud_index_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_note": "ncu dram__bytes_read+write of one launch at this workload (profiles/ncu_summary_r01.json); "
+                                "the reference's 16-byte pcl::PointXYZ records carry 4 padding bytes per point, so traffic "
+                                "= 16/12 x algorithmic + boxes",
                 "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": B * b_knn,
                 "as_laid_out_16B_GBps": B * 16 * npts / (index_ms_avg * 1e-3) / 1e9,
@@ -360,7 +370,7 @@ def main():
     ap.add_argument("--npts", type=int, default=50000)
     ap.add_argument("--warm", default="ref", choices=["ref", "cold"])
     ap.add_argument("--tol", type=float, default=1e-8)
-    ap.add_argument("--max-iter", type=int, default=100)
+    ap.add_argument("--max-iter", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unorganised", action="store_true", help="do not pass the image row pitch to the index")
     args = ap.parse_args()
