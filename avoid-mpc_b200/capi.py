@@ -40,7 +40,7 @@ class Config(C.Structure):
 class SolverOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("max_iter", C.c_int32), ("mu_init", C.c_double),
                 ("bound_push", C.c_double), ("bound_frac", C.c_double), ("eps_min", C.c_double),
-                ("eps_scale", C.c_double)]
+                ("eps_scale", C.c_double), ("kappa_eps", C.c_double)]
 
 
 INFO_DTYPE = np.dtype([("cost", "f8"), ("kkt_dual", "f8"), ("kkt_compl", "f8"), ("mu", "f8"),

@@ -154,6 +154,7 @@ void refresh_consts(ampc_handle *h) {
     c.bound_frac = h->opts.bound_frac;
     c.eps_min = h->opts.eps_min;
     c.eps_scale = h->opts.eps_scale;
+    c.kappa_eps = h->opts.kappa_eps;
     c.max_iter = h->opts.max_iter;
     c.N = h->cfg.N;
     c.K = h->cfg.K;
@@ -415,6 +416,7 @@ void ampc_default_solver_opts(ampc_solver_opts *o) {
     o->bound_frac = 1e-2;
     o->eps_min = 1e-5;
     o->eps_scale = 1.0;
+    o->kappa_eps = 100.0;
 }
 
 int ampc_create(const ampc_config *cfg, ampc_handle **out) {
@@ -552,7 +554,7 @@ int ampc_set_accel_limits(ampc_handle *h, double a_min_z, double a_max_z, double
 }
 int ampc_set_solver_opts(ampc_handle *h, const ampc_solver_opts *o) {
     if (!h || !o) return AMPC_ERR_INVALID;
-    if (!(o->tol > 0) || o->max_iter < 0 || !(o->mu_init > 0) || !(o->eps_min >= 0))
+    if (!(o->tol > 0) || o->max_iter < 0 || !(o->mu_init > 0) || !(o->eps_min >= 0) || !(o->kappa_eps > 0))
         return fail(h, AMPC_ERR_INVALID, "bad solver options");
     h->opts = *o;
     h->consts_dirty = true;

@@ -36,7 +36,7 @@ struct SolveConsts {
     double wgt[25];                    // [Q_goal(10) | Q_pen(10) | Q_u(4) | lambda]
     double radius;
     double lb[4], ub[4];
-    double tol, mu_init, bound_push, bound_frac, eps_min, eps_scale;
+    double tol, mu_init, bound_push, bound_frac, eps_min, eps_scale, kappa_eps;
     int32_t max_iter, N, K, n_prefix;
 };
 

@@ -292,6 +292,90 @@ __device__ double eval_cost(const WarpCtx &w, double eps) {
     return warp_sum(acc);
 }
 
+// Objective value only (line-search trials, final cost): the (N-1)*K collision terms are
+// spread over all 32 lanes (term t -> lane t mod 32; consecutive lanes read consecutive
+// obstacle points), the N control/path/terminal terms over lanes 0..N-1.
+template <bool TRIAL>
+__device__ double eval_value(const WarpCtx &w, double eps) {
+    const SolveConsts &c = *w.c;
+    const int N = c.N, K = c.K;
+    const double *s = w.s;
+    const WarpLayout &L = w.L;
+    const double *qg = c.wgt, *qp = c.wgt + 10, *qu = c.wgt + 20;
+    const double lam = c.wgt[24];
+    double acc = 0.0;
+    for (int kc = w.lane; kc < N; kc += 32) {
+        const int k = kc + 1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double uu = s[L.u + 4 * kc + i];
+            if (TRIAL)
+                uu += s[L.dut + 4 * kc + i];
+            const double d = uu - (i == 2 ? AMPC_GZ : 0.0);
+            acc += qu[i] * d * d;
+        }
+        double x[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            x[i] = s[L.x + 10 * k + i];
+            if (TRIAL)
+                x[i] += s[L.dxt + 10 * k + i];
+        }
+        if (kc == N - 1) {
+            const double *tg = w.prefix + 10 + 10 * N + 3 * K * N;
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+                const double d = x[i] - tg[i];
+                acc += qg[i] * d * d;
+            }
+        } else {
+            const double *ref = w.prefix + 10 + 10 * kc;
+            const double cy = s[L.cs + 2 * kc], sy = s[L.cs + 2 * kc + 1];
+            double dl[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i)
+                dl[i] = x[i] - ref[i];
+            const double rd0 = cy * dl[0] - sy * dl[1], rd1 = sy * dl[0] + cy * dl[1];
+            const double rd4 = cy * dl[4] - sy * dl[5], rd5 = sy * dl[4] + cy * dl[5];
+            acc += qp[0] * rd0 * rd0 + qp[1] * rd1 * rd1 + qp[4] * rd4 * rd4 + qp[5] * rd5 * rd5;
+            acc += qp[2] * dl[2] * dl[2] + qp[3] * dl[3] * dl[3] + qp[6] * dl[6] * dl[6] +
+                   qp[7] * dl[7] * dl[7] + qp[8] * dl[8] * dl[8] + qp[9] * dl[9] * dl[9];
+        }
+    }
+    const double far2 = (c.radius + 1.25) * (c.radius + 1.25);
+    const double *ob = w.prefix + 10 + 10 * N;
+    const int n_terms = (N - 1) * K;
+    int kc = 0, j = w.lane;
+    while (j >= K) {
+        j -= K;
+        ++kc;
+    }
+    for (int t = w.lane; t < n_terms; t += 32) {
+        const int k = kc + 1;
+        double px = s[L.x + 10 * k], py = s[L.x + 10 * k + 1], pz = s[L.x + 10 * k + 2];
+        double vx = s[L.x + 10 * k + 4], vy = s[L.x + 10 * k + 5], vz = s[L.x + 10 * k + 6];
+        if (TRIAL) {
+            px += s[L.dxt + 10 * k], py += s[L.dxt + 10 * k + 1], pz += s[L.dxt + 10 * k + 2];
+            vx += s[L.dxt + 10 * k + 4], vy += s[L.dxt + 10 * k + 5], vz += s[L.dxt + 10 * k + 6];
+        }
+        const double d0 = ob[3 * t] - px, d1 = ob[3 * t + 1] - py, d2 = ob[3 * t + 2] - pz;
+        const double r2 = d0 * d0 + d1 * d1 + d2 * d2;
+        if (r2 <= far2) { // same far-term rule as eval_cost
+            const double rr = sqrt(r2);
+            const double sv = (vx * d0 + vy * d1 + vz * d2) / rr;
+            const double e = exp((rr - c.radius) * -32.0);
+            const double sp = e < 7.450580596923828e-09 ? e : log(1.0 + e);
+            acc += lam * sp * (sqrt(sv * sv + eps * eps) - eps);
+        }
+        j += 32;
+        while (j >= K) {
+            j -= K;
+            ++kc;
+        }
+    }
+    return warp_sum(acc);
+}
+
 // Riccati backward sweep + adjoint.  Lane 4i+j (i,j = chains, lanes 16..31 mirror 0..15)
 // keeps the 3x3 block P^(ij) coupling chain i and chain j in registers; per stage
 //   S_ij = G_i' P^(ij) G_j (+R_i),  Bm^(i)_j = F_i' P^(ij) G_j,  A^(ij) = F_i' P^(ij) F_j,
@@ -545,7 +629,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
     const int N = c.N, lane = w.lane, nu = 4 * N;
     double *s = w.s;
     const WarpLayout &L = w.L;
-    const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+    const double kappa_eps = c.kappa_eps, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
     const double eta = 1e-4, kappa_sigma = 1e10;
     const double mu_min = c.tol / 10.0;
     double mu = c.mu_init, delta_last = 0.0;
@@ -720,7 +804,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
                 gdt += s[L.q + e] * s[L.dxt + e];
             bar = warp_sum(bar);
             gdt = warp_sum(gdt);
-            const double phit = eval_cost<false, true>(w, eps) - mu * bar;
+            const double phit = eval_value<true>(w, eps) - mu * bar;
             if (phit <= phi0 + eta * gdt + 10.0 * 2.220446049250313e-16 * fabs(phi0)) {
                 accepted = true;
                 break;
@@ -754,7 +838,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         __syncwarp();
     }
     // results: w = [X_0,U_0,...,X_N]; objective without smoothing
-    const double cost = eval_cost<false, false>(w, 0.0);
+    const double cost = eval_value<false>(w, 0.0);
     for (int e = lane; e < 10 * (N + 1); e += 32) {
         const int k = e / 10, i = e - 10 * k;
         w_inout[14 * k + i] = s[L.x + e];

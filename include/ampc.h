@@ -71,6 +71,8 @@ typedef struct ampc_solver_opts {
     double bound_frac; /*                                                default 1e-2 */
     double eps_min;    /* floor of the |v.n| smoothing, m/s              default 1e-5 */
     double eps_scale;  /* smoothing eps = max(eps_min, eps_scale*mu)     default 1.0  */
+    double kappa_eps;  /* barrier sub-problem tolerance: mu is reduced once the barrier KKT
+                          error is <= kappa_eps*mu (ipopt.barrier_tol_factor)  default 100 */
 } ampc_solver_opts;
 
 /* one record per instance written by the solve calls */

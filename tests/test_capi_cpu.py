@@ -29,7 +29,7 @@ def test_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(A.capi.Config) == 40
-    assert ctypes.sizeof(A.capi.SolverOpts) == 56
+    assert ctypes.sizeof(A.capi.SolverOpts) == 64
     assert A.capi.INFO_DTYPE.itemsize == 48
     o = A.capi.default_solver_opts()
     assert (o.tol, o.max_iter, o.mu_init, o.bound_push, o.eps_min) == (1e-8, 100, 0.1, 1e-2, 1e-5)
