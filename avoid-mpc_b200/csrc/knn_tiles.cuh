@@ -50,6 +50,21 @@ struct TileGeom {
             n_tiles = (n + KT_TILE - 1) / KT_TILE;
         }
     }
+    // record indices of slots `lane` and `lane + 32` of tile t (-1: empty slot); one division
+    __device__ void points2(int t, int lane, int n, int &i0, int &i1) const {
+        if (row_w > 0) {
+            const int ty = t / tiles_x, tx = t - ty * tiles_x;
+            const int col = 8 * tx + (lane & 7);
+            const int a = (8 * ty + (lane >> 3)) * row_w + col, b = a + 4 * row_w;
+            const bool ok = col < row_w;
+            i0 = ok && a < n ? a : -1;
+            i1 = ok && b < n ? b : -1;
+        } else {
+            const int a = t * KT_TILE + lane, b = a + 32;
+            i0 = a < n ? a : -1;
+            i1 = b < n ? b : -1;
+        }
+    }
     // record index of slot s (0..63) of tile t, or -1 if the slot is empty
     __host__ __device__ int point(int t, int s, int n) const {
         int i;
@@ -383,7 +398,8 @@ __device__ __forceinline__ void topk_insert(TopK &e, int k, double d, uint32_t i
 __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const TileGeom &g, int tile,
                                           double qx, double qy, double qz, TopK &e, double &kth, int k,
                                           int lane) {
-    const int i0 = g.point(tile, lane, n), i1 = g.point(tile, lane + 32, n);
+    int i0, i1;
+    g.points2(tile, lane, n, i0, i1);
     double d0 = INFINITY, d1 = INFINITY;
     if (i0 >= 0) {
         const float4 p = knn_ldg(cloud + i0);
@@ -442,6 +458,39 @@ __device__ __forceinline__ void knn_write_result(const KnnParams &P, const float
     if (P.count && lane == 0) P.count[(int64_t)b * P.Q + q] = cnt;
 }
 
+// Conservative single-precision bounds for the pruning tests (FP32 issues at twice the
+// FP64 rate): every operation is rounded toward the safe side (query widened to the float
+// interval [qlo, qhi], differences/products/sums rounded down for the lower bound and up
+// for the upper bound) and a final factor (1 -+ 2^-20) absorbs the round-to-nearest of
+// the double-precision distance itself.  lb32 <= knn_dist2(q, p) <= ub32 for every p in
+// the box; only the tightness of the pruning differs from the double version.
+struct QueryF {
+    float xlo, xhi, ylo, yhi, zlo, zhi;
+};
+__device__ __forceinline__ QueryF make_queryf(double x, double y, double z) {
+    QueryF q;
+    q.xlo = __double2float_rd(x), q.xhi = __double2float_ru(x);
+    q.ylo = __double2float_rd(y), q.yhi = __double2float_ru(y);
+    q.zlo = __double2float_rd(z), q.zhi = __double2float_ru(z);
+    return q;
+}
+__device__ __forceinline__ float knn_box_lb32(const QueryF &q, float lx, float ly, float lz, float hx,
+                                              float hy, float hz) {
+    const float ax = fmaxf(fmaxf(__fsub_rd(lx, q.xhi), __fsub_rd(q.xlo, hx)), 0.f);
+    const float ay = fmaxf(fmaxf(__fsub_rd(ly, q.yhi), __fsub_rd(q.ylo, hy)), 0.f);
+    const float az = fmaxf(fmaxf(__fsub_rd(lz, q.zhi), __fsub_rd(q.zlo, hz)), 0.f);
+    const float r = __fadd_rd(__fadd_rd(__fmul_rd(ax, ax), __fmul_rd(ay, ay)), __fmul_rd(az, az));
+    return __fmul_rd(r, 0.99999904632568359375f); // 1 - 2^-20
+}
+__device__ __forceinline__ float knn_box_ub32(const QueryF &q, float lx, float ly, float lz, float hx,
+                                              float hy, float hz) {
+    const float ax = fmaxf(fabsf(__fsub_ru(q.xhi, lx)), fabsf(__fsub_rd(q.xlo, hx)));
+    const float ay = fmaxf(fabsf(__fsub_ru(q.yhi, ly)), fabsf(__fsub_rd(q.ylo, hy)));
+    const float az = fmaxf(fabsf(__fsub_ru(q.zhi, lz)), fabsf(__fsub_rd(q.zlo, hz)));
+    const float r = __fadd_ru(__fadd_ru(__fmul_ru(ax, ax), __fmul_ru(ay, ay)), __fmul_ru(az, az));
+    return __fmul_ru(r, 1.00000095367431640625f); // 1 + 2^-20
+}
+
 // Upper bound of knn_dist2 over every point inside the box (farthest corner).
 __device__ __forceinline__ double knn_box_ub(double qx, double qy, double qz, float lx, float ly,
                                              float lz, float hx, float hy, float hz) {
@@ -454,9 +503,9 @@ __device__ __forceinline__ double knn_box_ub(double qx, double qy, double qz, fl
     return r;
 }
 
-__global__ void __launch_bounds__(KS_WARPS * 32)
+__global__ void __launch_bounds__(KS_WARPS * 32, 6)
 knn_search_kernel(const KnnParams P) {
-    __shared__ double sLB[KS_WARPS][KS_CHUNK];       // lower bound per tile of the chunk (NaN = done)
+    __shared__ float sLB[KS_WARPS][KS_CHUNK];        // conservative lower bound per tile (NaN = done)
     __shared__ unsigned short sCand[KS_WARPS][KS_CHUNK]; // compacted list of tiles worth visiting
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y, seg = blockIdx.z;
@@ -473,7 +522,8 @@ knn_search_kernel(const KnnParams P) {
     const int n_tiles = g.n_tiles;
     const int per = (n_tiles + P.segs - 1) / P.segs;
     const int t_begin = seg * per, t_end = min(n_tiles, t_begin + per);
-    double *lbuf = sLB[warp];
+    float *lbuf = sLB[warp];
+    const QueryF qf = make_queryf(qx, qy, qz);
     unsigned short *cand = sCand[warp];
     TopK e{INFINITY, 0xffffffffu};
     // `bound`: no point farther than this can be among the k nearest.  It is the min of
@@ -487,16 +537,16 @@ knn_search_kernel(const KnnParams P) {
         for (int j = lane; j < cn; j += 32) {
             const float4 a = knn_ldg(boxes + 2 * (int64_t)(c0 + j));
             const float4 h = knn_ldg(boxes + 2 * (int64_t)(c0 + j) + 1);
-            lbuf[j] = knn_box_lb(qx, qy, qz, a.x, a.y, a.z, a.w, h.x, h.y);
+            lbuf[j] = knn_box_lb32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
             if (__float_as_int(h.z) >= k) // the tile alone holds >= k points within its farthest corner
-                ubmin = fmin(ubmin, knn_box_ub(qx, qy, qz, a.x, a.y, a.z, a.w, h.x, h.y));
+                ubmin = fmin(ubmin, (double)knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y));
         }
         bound = fmin(bound, warp_min(ubmin));
         __syncwarp();
         // compact the tiles that can still matter
         int m = 0;
         for (int j0 = 0; j0 < cn; j0 += 32) {
-            const bool keep = (j0 + lane < cn) && lbuf[j0 + lane] <= bound;
+            const bool keep = (j0 + lane < cn) && (double)lbuf[j0 + lane] <= bound;
             const unsigned mk = __ballot_sync(AMPC_FULL_MASK, keep);
             if (keep)
                 cand[m + __popc(mk & ((1u << lane) - 1u))] = (unsigned short)(j0 + lane);
@@ -508,7 +558,7 @@ knn_search_kernel(const KnnParams P) {
             double best = INFINITY;
             int best_c = -1;
             for (int c = lane; c < m; c += 32) {
-                const double lb = lbuf[cand[c]];
+                const double lb = (double)lbuf[cand[c]];
                 if (lb < best) { // NaN (already visited) never wins
                     best = lb;
                     best_c = c;
@@ -536,7 +586,7 @@ knn_search_kernel(const KnnParams P) {
         // ... then one sweep over the remaining candidates in storage order
         for (int cb = 0; cb < m; cb += 32) {
             const int j = (cb + lane < m) ? (int)cand[cb + lane] : 0;
-            const double lb = (cb + lane < m) ? lbuf[j] : NAN;
+            const double lb = (cb + lane < m) ? (double)lbuf[j] : NAN;
             unsigned mk = __ballot_sync(AMPC_FULL_MASK, lb <= bound);
             while (mk) {
                 const int src = __ffs(mk) - 1;

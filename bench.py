@@ -360,6 +360,59 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_knn_sweep(args):
+    """BASELINE config C4: k-NN only, cloud sizes 10k..1M points, Q=20, K=16, ~2 GB of clouds per
+    GPU; achieved GB/s of the k-NN stage (index build + search) against the measured HBM peak."""
+    import torch
+    import avoid_mpc_b200 as A
+    S = A.synth
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream().cuda_stream
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6650.0
+    rows = []
+    for npts in (10000, 20000, 50000, 100000, 200000, 500000, 1000000):
+        B = int(min(4096, max(8, 2e9 // (16 * npts))))
+        ids = list(range(B))
+        clouds = S.forest_clouds_torch(ids, npts, dev)
+        _, ref, _ = S.states_batch(ids, N_H, DT)
+        q = torch.tensor(np.ascontiguousarray(ref[:, :, :3]), device=dev)
+        h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=npts, device=local)
+        h.cloud_set_layout(S.image_shape(npts)[0])
+        h.cloud_set_batch_dev(clouds, stream=stream)
+        idx = torch.empty((B, N_H, K_NB), dtype=torch.int32, device=dev)
+        d2 = torch.empty((B, N_H, K_NB), dtype=torch.float64, device=dev)
+        cnt = torch.empty((B, N_H), dtype=torch.int32, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ti, ts = [], []
+        for it in range(3 + args.steps):
+            ev[0].record()
+            h.cloud_index_dev(0, B, stream=stream)
+            ev[1].record()
+            h.knn_dev(q, K_NB, idx, d2, None, cnt, stream=stream)
+            ev[2].record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                ti.append(ev[0].elapsed_time(ev[1]))
+                ts.append(ev[1].elapsed_time(ev[2]))
+        b_knn = 12 * npts + N_H * (24 + K_NB * 12)
+        t_i, t_s = statistics.median(ti), statistics.median(ts)
+        rows.append({"npts": npts, "batch": B, "index_ms": t_i, "search_ms": t_s,
+                     "index_GBps": B * b_knn / (t_i * 1e-3) / 1e9, "index_frac": B * b_knn / (t_i * 1e-3) / 1e9 / hbm_peak,
+                     "stage_GBps": B * b_knn / ((t_i + t_s) * 1e-3) / 1e9,
+                     "stage_frac": B * b_knn / ((t_i + t_s) * 1e-3) / 1e9 / hbm_peak,
+                     "as_laid_out_16B_index_GBps": B * 16 * npts / (t_i * 1e-3) / 1e9,
+                     "scene_rounds_per_s": B / ((t_i + t_s) * 1e-3)})
+        h.close()
+        del clouds
+        torch.cuda.empty_cache()
+    print(json.dumps({"mode": "knn_sweep", "unit": "GB/s", "peak": hbm_peak, "Q": N_H, "K": K_NB, "rows": rows}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,10 +426,13 @@ def main():
     ap.add_argument("--max-iter", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unorganised", action="store_true", help="do not pass the image row pitch to the index")
+    ap.add_argument("--mode", default="solves", choices=["solves", "knn_sweep"])
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
+    if args.mode == "knn_sweep":
+        run_knn_sweep(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_ours(args)
