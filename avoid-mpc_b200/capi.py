@@ -25,7 +25,7 @@ SYMBOLS = [
     "ampc_default_solver_opts", "ampc_set_solver_opts", "ampc_get_dynamics",
     "ampc_cloud_set", "ampc_cloud_set_batch", "ampc_cloud_set_batch_dev", "ampc_cloud_index_dev", "ampc_cloud_set_layout", "ampc_cloud_count",
     "ampc_knn_batch", "ampc_knn_batch_dev", "ampc_solve_batch", "ampc_solve_batch_dev",
-    "ampc_round_batch", "ampc_round_batch_dev", "ampc_last_prefix_dev",
+    "ampc_round_batch", "ampc_round_batch_dev", "ampc_tick_batch", "ampc_tick_batch_dev", "ampc_last_prefix_dev",
     "ampc_best_of", "ampc_best_of_dev", "ampc_launch_count", "ampc_stream", "ampc_synchronize",
     "ampc_profile_enable", "ampc_profile_get",
 ]
@@ -104,6 +104,10 @@ def lib():
         L.ampc_round_batch.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp]
         L.ampc_round_batch_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp]
         L.ampc_last_prefix_dev.argtypes = [_vp, C.POINTER(_vp)]
+        L.ampc_tick_batch.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int32,
+                                      _vp, _vp, _vp, _vp]
+        L.ampc_tick_batch_dev.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp, C.c_double, C.c_double, C.c_int32,
+                                          _vp, _vp, _vp, _vp, _vp]
         L.ampc_best_of.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp]
         L.ampc_best_of_dev.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
         L.ampc_launch_count.restype = C.c_int64
@@ -296,6 +300,28 @@ class Handle:
         self._ck(self.L.ampc_round_batch_dev(self.h, B, _ptr(scene_of_dev), _ptr(x0_dev), _ptr(ref_dev),
                                              _ptr(pos_x_dev), speed, safety_distance, _ptr(w_dev),
                                              _ptr(info_dev), _ptr(replan_dev), stream))
+
+    def tick(self, x0, ref, w0, scene_of=None, pos_x=None, speed=10.0, safety_distance=0.2, max_rounds=3):
+        """One control tick (<= max_rounds rounds on the device). Returns (w, ref, info, rounds, is_safety)."""
+        x0 = _f64(x0).reshape(-1, 10)
+        B = x0.shape[0]
+        ref = np.array(ref, dtype=np.float64).reshape(B, self.N, 10).copy()
+        w = np.array(w0, dtype=np.float64).reshape(B, self.n_w).copy()
+        so = None if scene_of is None else np.ascontiguousarray(scene_of, dtype=np.int32)
+        px = None if pos_x is None else _f64(pos_x, (B,))
+        info = np.zeros(B, dtype=INFO_DTYPE)
+        rounds = np.zeros(B, dtype=np.int32)
+        safe = np.zeros(B, dtype=np.int32)
+        self._ck(self.L.ampc_tick_batch(self.h, B, _ptr(so), x0.ctypes.data, ref.ctypes.data, _ptr(px), speed,
+                                        safety_distance, max_rounds, w.ctypes.data, info.ctypes.data,
+                                        rounds.ctypes.data, safe.ctypes.data))
+        return w, ref, info, rounds, safe
+
+    def tick_dev(self, B, x0_dev, ref_dev, w_dev, info_dev=None, rounds_dev=None, safe_dev=None, scene_of_dev=None,
+                 pos_x_dev=None, speed=10.0, safety_distance=0.2, max_rounds=3, stream=None):
+        self._ck(self.L.ampc_tick_batch_dev(self.h, B, _ptr(scene_of_dev), _ptr(x0_dev), _ptr(ref_dev),
+                                            _ptr(pos_x_dev), speed, safety_distance, max_rounds, _ptr(w_dev),
+                                            _ptr(info_dev), _ptr(rounds_dev), _ptr(safe_dev), stream))
 
     def last_prefix_ptr(self):
         p = _vp()

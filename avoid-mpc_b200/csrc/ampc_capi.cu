@@ -68,6 +68,7 @@ struct ampc_handle {
     DevBuf queries, prefix, w, info, knn_idx, knn_d2, knn_cnt, knn_pts, scene_of, x0, ref, posx, replan;
     DevBuf ws_d, ws_i, ws_counter;
     DevBuf bo_arg, bo_cost;
+    DevBuf tk_active, tk_q0, tk_d1, tk_c1, tk_ep, tk_ec, tk_ed, tk_safe, tk_rounds; // tick loop
     int64_t launches = 0;
     std::string err;
     int solve_smem_set = 0;
@@ -276,6 +277,81 @@ int prof_end(ampc_handle *h, int slot, cudaStream_t st) {
     return AMPC_OK;
 }
 
+// ---- control-tick loop on the device (AvoidanceStateMachine.cpp:328-344) --------------
+// PlanWapionts (:259-281) for waypoint 0 of every still-active instance: if an obstacle is
+// within safety_distance, move the waypoint to the nearest Edge point; no Edge point ->
+// isSafety = false.  d1/cnt1: 1-NN on the Obstacle cloud, e*: 1-NN on the Edge cloud.
+__global__ void tick_plan_kernel(int B, int N, const int32_t *active, const double *d1, const int32_t *cnt1,
+                                 const double *epts, const int32_t *ecnt, bool have_edge, double safety,
+                                 double *ref, int32_t *is_safety) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || active[b] == 0)
+        return;
+    int safe = 1;
+    // GetNearestDistance returns sqrt(min dist2), or DBL_MAX when nothing was found (:400-427)
+    const double nearest = cnt1[b] > 0 ? sqrt(d1[b]) : 1.7976931348623157e308;
+    if (nearest <= safety) {
+        if (have_edge && ecnt[b] > 0) {
+            double *r0 = ref + (int64_t)b * N * 10;
+            r0[0] = epts[3 * b], r0[1] = epts[3 * b + 1], r0[2] = epts[3 * b + 2];
+        } else {
+            safe = 0;
+        }
+    }
+    is_safety[b] = safe;
+}
+// first waypoint of every instance as a 1-query site
+__global__ void tick_site0_kernel(int B, int N, const double *ref, double *q0) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B)
+        return;
+    const double *r0 = ref + (int64_t)b * N * 10;
+    q0[3 * b] = r0[0], q0[3 * b + 1] = r0[1], q0[3 * b + 2] = r0[2];
+}
+// `if (!needReplan && iter > 0 && isSafety) break;` (:333) as a per-instance mask update
+__global__ void tick_gate_kernel(int B, int iter, const int32_t *need_replan, const int32_t *is_safety,
+                                 int32_t *active, int32_t *rounds) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || active[b] == 0)
+        return;
+    if (!need_replan[b] && iter > 0 && is_safety[b])
+        active[b] = 0;
+    else
+        rounds[b] += 1;
+}
+// mRefPath[i] := x0Array[i][0:10] for i < N (:338-342) of the instances that just solved
+__global__ void tick_ref_update_kernel(int B, int N, const int32_t *active, const double *w, double *ref) {
+    const int b = blockIdx.x;
+    if (b >= B || active[b] == 0)
+        return;
+    for (int e = threadIdx.x; e < 10 * N; e += blockDim.x) {
+        const int i = e / 10, c = e - 10 * i;
+        ref[(int64_t)b * N * 10 + e] = w[(int64_t)b * (10 + 14 * N) + 14 * i + c];
+    }
+}
+__global__ void tick_init_kernel(int B, int32_t *active, int32_t *rounds, int32_t *is_safety) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        active[b] = 1;
+        rounds[b] = 0;
+        is_safety[b] = 1;
+    }
+}
+// replan flags of the active instances only (inactive keep their last value)
+__global__ void tick_replan_kernel(int B, int Q, int k, const int32_t *active, const double *dist2,
+                                   const int32_t *count, double safety, int32_t *need_replan) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B || active[b] == 0)
+        return;
+    int flag = 0;
+    for (int q = 0; q < Q; ++q) {
+        const int c = count[(int64_t)b * Q + q];
+        if (c == 0 || sqrt(dist2[((int64_t)b * Q + q) * k]) <= safety)
+            flag = 1;
+    }
+    need_replan[b] = flag;
+}
+
 int check_kind(ampc_handle *h, int kind) {
     if (kind != AMPC_CLOUD_OBSTACLE && kind != AMPC_CLOUD_EDGE)
         return fail(h, AMPC_ERR_INVALID, "kind must be AMPC_CLOUD_OBSTACLE or AMPC_CLOUD_EDGE");
@@ -286,7 +362,7 @@ int check_kind(ampc_handle *h, int kind) {
 
 int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, const double *q_dev,
                int Q, int k, int32_t *idx, double *d2, int32_t *cnt, double *pts, int64_t pts_is,
-               int64_t pts_qs, cudaStream_t st) {
+               int64_t pts_qs, cudaStream_t st, const int32_t *active = nullptr) {
     if (k < 1 || k > KNN_KMAX)
         return fail(h, AMPC_ERR_UNSUPPORTED, "k must be in 1..32");
     if (Q < 1 || B < 1)
@@ -310,6 +386,7 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     P.slot_tiles = h->slot_tiles[kind];
     P.row_w = h->row_w[kind];
     P.scene_of = scene_of_dev;
+    P.active = active;
     P.queries = q_dev;
     P.Q = Q;
     P.k = k;
@@ -367,7 +444,7 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
 constexpr int SOLVE_WARPS = 2;
 
 int launch_solve(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
-                 cudaStream_t st) {
+                 cudaStream_t st, const int32_t *active = nullptr) {
     refresh_consts(h);
     const size_t smem = solve_smem_bytes(h->cfg.N, SOLVE_WARPS);
     if (smem > 227 * 1024)
@@ -377,7 +454,7 @@ int launch_solve(ampc_handle *h, int B, const double *prefix_dev, double *w_dev,
         h->solve_smem_set = (int)smem;
     }
     const int grid = (B + SOLVE_WARPS - 1) / SOLVE_WARPS;
-    ipm_solve_kernel<SOLVE_WARPS><<<grid, SOLVE_WARPS * 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev);
+    ipm_solve_kernel<SOLVE_WARPS><<<grid, SOLVE_WARPS * 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active);
     h->launches++;
     CK(cudaGetLastError());
     return AMPC_OK;
@@ -508,7 +585,8 @@ void ampc_destroy(ampc_handle *h) {
     DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
-                     &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost};
+                     &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
+                     &h->tk_c1, &h->tk_ep, &h->tk_ec, &h->tk_ed, &h->tk_safe, &h->tk_rounds};
     for (DevBuf *b : all)
         b->release();
     for (auto &e : h->prof_ev) cudaEventDestroy(e);
@@ -874,6 +952,119 @@ int ampc_round_batch(ampc_handle *h, int32_t B, const int32_t *scene_of, const d
         CK(cudaMemcpyAsync(info_out, h->info.p, (size_t)B * sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
     if (need_replan_out)
         CK(cudaMemcpyAsync(need_replan_out, h->replan.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMPC_OK;
+}
+
+// ---- one control tick: up to max_rounds rounds with the reference's early exit ----------
+int ampc_tick_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev, const double *x0_dev,
+                        double *ref_inout_dev, const double *pos_x_dev, double speed,
+                        double safety_distance, int32_t max_rounds, double *w_inout_dev,
+                        ampc_solve_info *info_dev, int32_t *rounds_dev, int32_t *is_safety_dev,
+                        void *stream) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    rc = check_kind(h, AMPC_CLOUD_OBSTACLE);
+    if (rc) return rc;
+    if (!x0_dev || !ref_inout_dev || !w_inout_dev) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    if (h->cfg.K < 1 || max_rounds < 1) return fail(h, AMPC_ERR_INVALID, "tick needs K >= 1 and max_rounds >= 1");
+    if (!scene_of_dev && B > h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "identity scene map needs B <= max_scenes");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cfg.N, K = h->cfg.K;
+    const bool have_edge = h->slot_points[AMPC_CLOUD_EDGE] > 0;
+    const size_t Bs = (size_t)B;
+    CK(h->tk_active.reserve(Bs * 4));
+    CK(h->tk_q0.reserve(Bs * 24));
+    CK(h->tk_d1.reserve(Bs * 8));
+    CK(h->tk_c1.reserve(Bs * 4));
+    CK(h->tk_ep.reserve(Bs * 24));
+    CK(h->tk_ec.reserve(Bs * 4));
+    CK(h->tk_ed.reserve(Bs * 8));
+    CK(h->tk_safe.reserve(Bs * 4));
+    CK(h->tk_rounds.reserve(Bs * 4));
+    int32_t *active = h->tk_active.as<int32_t>();
+    int32_t *safe = is_safety_dev ? is_safety_dev : h->tk_safe.as<int32_t>();
+    int32_t *rounds = rounds_dev ? rounds_dev : h->tk_rounds.as<int32_t>();
+    int32_t *replan = h->replan.as<int32_t>();
+    SolveOut *info = info_dev ? reinterpret_cast<SolveOut *>(info_dev) : h->info.as<SolveOut>();
+    double *prefix = h->prefix.as<double>();
+    const int tb = 128, gb = (B + tb - 1) / tb;
+    tick_init_kernel<<<gb, tb, 0, st>>>(B, active, rounds, safe);
+    h->launches++;
+    for (int iter = 0; iter < max_rounds; ++iter) {
+        // PlanWapionts: 1-NN of waypoint 0 on the Obstacle cloud, then on the Edge cloud
+        tick_site0_kernel<<<gb, tb, 0, st>>>(B, N, ref_inout_dev, h->tk_q0.as<double>());
+        h->launches++;
+        rc = launch_knn(h, AMPC_CLOUD_OBSTACLE, B, scene_of_dev, h->tk_q0.as<double>(), 1, 1, nullptr,
+                        h->tk_d1.as<double>(), h->tk_c1.as<int32_t>(), nullptr, 0, 0, st, active);
+        if (rc) return rc;
+        if (have_edge) {
+            rc = launch_knn(h, AMPC_CLOUD_EDGE, B, scene_of_dev, h->tk_q0.as<double>(), 1, 1, nullptr,
+                            h->tk_ed.as<double>(), h->tk_ec.as<int32_t>(), h->tk_ep.as<double>(), 3, 3, st, active);
+            if (rc) return rc;
+        }
+        tick_plan_kernel<<<gb, tb, 0, st>>>(B, N, active, h->tk_d1.as<double>(), h->tk_c1.as<int32_t>(),
+                                            h->tk_ep.as<double>(), h->tk_ec.as<int32_t>(), have_edge,
+                                            safety_distance, ref_inout_dev, safe);
+        h->launches++;
+        // ProcessWaypoints + GetRefStates
+        pack_prefix_kernel<<<B, 64, 0, st>>>(B, N, K, x0_dev, ref_inout_dev, pos_x_dev, speed, N * h->cfg.dt,
+                                             prefix, h->n_prefix, h->queries.as<double>());
+        h->launches++;
+        rc = launch_knn(h, AMPC_CLOUD_OBSTACLE, B, scene_of_dev, h->queries.as<double>(), N, K,
+                        h->knn_idx.as<int32_t>(), h->knn_d2.as<double>(), h->knn_cnt.as<int32_t>(),
+                        prefix + 10 + 10 * N, h->n_prefix, 3 * K, st, active);
+        if (rc) return rc;
+        tick_replan_kernel<<<gb, tb, 0, st>>>(B, N, K, active, h->knn_d2.as<double>(), h->knn_cnt.as<int32_t>(),
+                                              safety_distance, replan);
+        h->launches++;
+        tick_gate_kernel<<<gb, tb, 0, st>>>(B, iter, replan, safe, active, rounds);
+        h->launches++;
+        // Solve + hand the solution over as the next reference path / query sites
+        rc = launch_solve(h, B, prefix, w_inout_dev, info, st, active);
+        if (rc) return rc;
+        tick_ref_update_kernel<<<B, 64, 0, st>>>(B, N, active, w_inout_dev, ref_inout_dev);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return AMPC_OK;
+}
+
+int ampc_tick_batch(ampc_handle *h, int32_t B, const int32_t *scene_of, const double *x0, double *ref_inout,
+                    const double *pos_x, double speed, double safety_distance, int32_t max_rounds,
+                    double *w_inout, ampc_solve_info *info_out, int32_t *rounds_out, int32_t *is_safety_out) {
+    int rc = check_batch(h, B);
+    if (rc) return rc;
+    if (!x0 || !ref_inout || !w_inout) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    if (scene_of)
+        for (int b = 0; b < B; ++b)
+            if (scene_of[b] < 0 || scene_of[b] >= h->cfg.max_scenes)
+                return fail(h, AMPC_ERR_CAPACITY, "scene_of entry out of range");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t N = h->cfg.N;
+    CK(h->tk_safe.reserve((size_t)B * 4));
+    CK(h->tk_rounds.reserve((size_t)B * 4));
+    CK(cudaMemcpyAsync(h->x0.p, x0, (size_t)B * 10 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ref.p, ref_inout, (size_t)B * N * 10 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->w.p, w_inout, (size_t)B * h->n_w * 8, cudaMemcpyHostToDevice, st));
+    if (scene_of) CK(cudaMemcpyAsync(h->scene_of.p, scene_of, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    if (pos_x) CK(cudaMemcpyAsync(h->posx.p, pos_x, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    rc = ampc_tick_batch_dev(h, B, scene_of ? h->scene_of.as<int32_t>() : nullptr, h->x0.as<double>(),
+                             h->ref.as<double>(), pos_x ? h->posx.as<double>() : nullptr, speed, safety_distance,
+                             max_rounds, h->w.as<double>(), reinterpret_cast<ampc_solve_info *>(h->info.p),
+                             h->tk_rounds.as<int32_t>(), h->tk_safe.as<int32_t>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(w_inout, h->w.p, (size_t)B * h->n_w * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ref_inout, h->ref.p, (size_t)B * N * 10 * 8, cudaMemcpyDeviceToHost, st));
+    if (info_out)
+        CK(cudaMemcpyAsync(info_out, h->info.p, (size_t)B * sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
+    if (rounds_out)
+        CK(cudaMemcpyAsync(rounds_out, h->tk_rounds.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (is_safety_out)
+        CK(cudaMemcpyAsync(is_safety_out, h->tk_safe.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return AMPC_OK;
 }

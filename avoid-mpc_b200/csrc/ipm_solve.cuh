@@ -860,7 +860,8 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double *__restrict__ prefix,
-                 double *__restrict__ w_inout, SolveOut *__restrict__ info) {
+                 double *__restrict__ w_inout, SolveOut *__restrict__ info,
+                 const int32_t *__restrict__ active /* nullable: instances with 0 are skipped */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SolveConsts *sc = reinterpret_cast<SolveConsts *>(smem_raw);
     double *wbase = reinterpret_cast<double *>(smem_raw + ((sizeof(SolveConsts) + 127) / 128) * 128);
@@ -873,7 +874,7 @@ ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * WARPS + warp;
-    if (b >= B)
+    if (b >= B || (active && active[b] == 0))
         return;
     const WarpLayout L(sc->N);
     WarpCtx ctx(sc, wbase + (size_t)warp * L.total, prefix + (size_t)b * sc->n_prefix, lane);

@@ -93,6 +93,7 @@ struct KnnParams {
     int64_t slot_tiles;
     int32_t row_w;           // 0: unorganised cloud; >0: row pitch for 8x8 patch tiles
     const int32_t *scene_of; // [B] or nullptr (identity)
+    const int32_t *active;   // [B] or nullptr: instances with 0 are skipped (outputs untouched)
     const double *queries;   // [B][Q][3]
     int32_t Q, k, segs;
     int32_t *idx;            // [B][Q][k] or nullptr
@@ -509,7 +510,7 @@ knn_search_kernel(const KnnParams P) {
     __shared__ unsigned short sCand[KS_WARPS][KS_CHUNK]; // compacted list of tiles worth visiting
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y, seg = blockIdx.z;
-    if (q >= P.Q)
+    if (q >= P.Q || (P.active && P.active[b] == 0))
         return;
     const int k = P.k;
     const int scene = P.scene_of ? P.scene_of[b] : b;
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(KS_WARPS * 32)
 knn_merge_kernel(const KnnParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y;
-    if (q >= P.Q)
+    if (q >= P.Q || (P.active && P.active[b] == 0))
         return;
     const int k = P.k;
     const int scene = P.scene_of ? P.scene_of[b] : b;

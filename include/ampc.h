@@ -184,6 +184,27 @@ int ampc_round_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev,
                          const double *x0_dev, const double *ref_dev, const double *pos_x_dev,
                          double speed, double safety_distance, double *w_inout_dev,
                          ampc_solve_info *info_dev, int32_t *need_replan_dev, void *stream);
+/* ---- one control tick for B instances: the TASK loop of AvoidanceStateMachine::Step
+ * (src/AvoidanceStateMachine.cpp:328-344) entirely on the device, no host round trip
+ * between rounds.  Per round and per still-active instance: PlanWapionts (:259-281: if
+ * waypoint 0 is within safety_distance of the Obstacle cloud it moves to the nearest Edge
+ * point; no Edge point -> isSafety = 0), ProcessWaypoints + GetRefStates + Solve, then the
+ * solved states become the next reference path and query sites (:338-342).  An instance
+ * stops before the solve of round iter > 0 when it needs no replan and is safe (:333).
+ *   ref_inout[B*N*10]  mRefPath after GetInitPath in; the last solved path out
+ *   x0[B*10]           mVecStateQuad (the caller does the latency extrapolation, :183-203)
+ *   rounds_out[B]      solves performed (1..max_rounds); is_safety_out[B]: 0 -> the caller
+ *                      publishes the slow-down command (:347-349).  Both may be NULL.
+ * u of PubCmd is w_inout[b*n_w + 10 .. 14). */
+int ampc_tick_batch(ampc_handle *h, int32_t B, const int32_t *scene_of, const double *x0,
+                    double *ref_inout, const double *pos_x, double speed, double safety_distance,
+                    int32_t max_rounds, double *w_inout, ampc_solve_info *info_out,
+                    int32_t *rounds_out, int32_t *is_safety_out);
+int ampc_tick_batch_dev(ampc_handle *h, int32_t B, const int32_t *scene_of_dev, const double *x0_dev,
+                        double *ref_inout_dev, const double *pos_x_dev, double speed,
+                        double safety_distance, int32_t max_rounds, double *w_inout_dev,
+                        ampc_solve_info *info_dev, int32_t *rounds_dev, int32_t *is_safety_dev,
+                        void *stream);
 /* device address of the packed prefixes of the last round (B*n_prefix doubles) */
 int ampc_last_prefix_dev(ampc_handle *h, const double **p_prefix_dev);
 
