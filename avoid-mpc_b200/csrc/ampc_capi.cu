@@ -8,6 +8,7 @@
 #include "knn_tiles.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -71,7 +72,8 @@ struct ampc_handle {
     DevBuf tk_active, tk_q0, tk_d1, tk_c1, tk_ep, tk_ec, tk_ed, tk_safe, tk_rounds; // tick loop
     int64_t launches = 0;
     std::string err;
-    int solve_smem_set = 0;
+    int solve_smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int solve_warps = 2;
     int knn_smem_set = 0;
     bool index_smem_set = false;
     // optional per-kernel timing of ampc_round_batch_dev (CUDA events on the caller's stream)
@@ -441,23 +443,38 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
     return prof_end(h, slot, st);
 }
 
-constexpr int SOLVE_WARPS = 2;
+template <int W>
+int launch_solve_w(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
+                   cudaStream_t st, const int32_t *active) {
+    const size_t smem = solve_smem_bytes(h->cfg.N, W);
+    if (smem > 227 * 1024)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "horizon too long for the per-warp shared-memory layout");
+    if ((int)smem > h->solve_smem_set[W]) {
+        CK(cudaFuncSetAttribute(ipm_solve_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->solve_smem_set[W] = (int)smem;
+    }
+    const int grid = (B + W - 1) / W;
+    ipm_solve_kernel<W><<<grid, W * 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active);
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
 
 int launch_solve(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
                  cudaStream_t st, const int32_t *active = nullptr) {
     refresh_consts(h);
-    const size_t smem = solve_smem_bytes(h->cfg.N, SOLVE_WARPS);
-    if (smem > 227 * 1024)
-        return fail(h, AMPC_ERR_UNSUPPORTED, "horizon too long for the per-warp shared-memory layout");
-    if ((int)smem > h->solve_smem_set) {
-        CK(cudaFuncSetAttribute(ipm_solve_kernel<SOLVE_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->solve_smem_set = (int)smem;
+    // warps (= instances) per CTA (AMPC_SOLVE_WARPS; measured best at C1: 2): the warps of a CTA start
+    // every iteration together (shared instruction cache); horizons too long for the per-warp
+    // shared memory of W warps fall back to fewer
+    int W = h->solve_warps;
+    while (W > 1 && solve_smem_bytes(h->cfg.N, W) > 227 * 1024)
+        W >>= 1;
+    switch (W) {
+    case 8: return launch_solve_w<8>(h, B, prefix_dev, w_dev, info_dev, st, active);
+    case 4: return launch_solve_w<4>(h, B, prefix_dev, w_dev, info_dev, st, active);
+    case 2: return launch_solve_w<2>(h, B, prefix_dev, w_dev, info_dev, st, active);
+    default: return launch_solve_w<1>(h, B, prefix_dev, w_dev, info_dev, st, active);
     }
-    const int grid = (B + SOLVE_WARPS - 1) / SOLVE_WARPS;
-    ipm_solve_kernel<SOLVE_WARPS><<<grid, SOLVE_WARPS * 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active);
-    h->launches++;
-    CK(cudaGetLastError());
-    return AMPC_OK;
 }
 
 int check_batch(ampc_handle *h, int B) {
@@ -525,6 +542,10 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
     h->n_w = 10 + 14 * cfg->N;
     h->n_prefix = 20 + 10 * cfg->N + 3 * cfg->K * cfg->N;
     ampc_default_solver_opts(&h->opts);
+    if (const char *e = std::getenv("AMPC_SOLVE_WARPS")) { // tuning knob: 1, 2, 4 or 8
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) h->solve_warps = v;
+    }
     // defaults of the reference constructor (src/HighLvlMpc.cpp:11-14,53-58)
     const double w0[25] = {100, 100, 100, 300, 1, 1, 1, 0., 0., 0., 0.0, 10, 10,
                            30,  0,   1,   1,   0., 0., 0., 1., 1., 1., 1., 1.};

@@ -133,7 +133,7 @@ struct WarpCtx {
 // lane = stage.  full: also writes q (grad x), r (grad u) and Hc (Hessian).
 // Returns the warp-wide objective value (identical in all lanes).
 template <bool FULL, bool TRIAL>
-__device__ double eval_cost(const WarpCtx &w, double eps) {
+__device__ __noinline__ double eval_cost(const WarpCtx &w, double eps) {
     const SolveConsts &c = *w.c;
     const int N = c.N, K = c.K;
     double *s = w.s;
@@ -295,8 +295,7 @@ __device__ double eval_cost(const WarpCtx &w, double eps) {
 // Objective value only (line-search trials, final cost): the (N-1)*K collision terms are
 // spread over all 32 lanes (term t -> lane t mod 32; consecutive lanes read consecutive
 // obstacle points), the N control/path/terminal terms over lanes 0..N-1.
-template <bool TRIAL>
-__device__ double eval_value(const WarpCtx &w, double eps) {
+__device__ __noinline__ double eval_value(const WarpCtx &w, double eps, const bool TRIAL) {
     const SolveConsts &c = *w.c;
     const int N = c.N, K = c.K;
     const double *s = w.s;
@@ -384,7 +383,7 @@ __device__ double eval_value(const WarpCtx &w, double eps) {
 // redundantly in every lane.  Returns false if a pivot of S is not positive (the reduced
 // Hessian has the wrong inertia) -> the caller regularises.  Also returns the dual
 // infeasibility |r_k + G'lam_{k+1} - zl + zu|_inf.
-__device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_out) {
+__device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_out) {
     const SolveConsts &c = *w.c;
     const int N = c.N;
     double *s = w.s;
@@ -550,7 +549,7 @@ __device__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_
 
 // forward sweep: du_k = K_k dx_k + kff_k, dx_{k+1} = Phi dx_k + Gam du_k, dx_0 = 0.
 // Lane 4i+j carries dx of chain i and of chain j.
-__device__ void riccati_forward(const WarpCtx &w) {
+__device__ __noinline__ void riccati_forward(const WarpCtx &w) {
     const SolveConsts &c = *w.c;
     const int N = c.N;
     double *s = w.s;
@@ -593,7 +592,7 @@ __device__ void riccati_forward(const WarpCtx &w) {
 }
 
 // dxt = linear roll-out of dut (dxt_0 = 0, dxt_{k+1} = Phi dxt_k + Gam dut_k); lane i < 4 = chain i
-__device__ void rollout_delta(const WarpCtx &w) {
+__device__ __noinline__ void rollout_delta(const WarpCtx &w) {
     const SolveConsts &c = *w.c;
     const int N = c.N;
     double *s = w.s;
@@ -624,12 +623,13 @@ struct SolveOut {
     int32_t iters, status, n_reg, n_backtrack;
 };
 
+template <bool SYNC>
 __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out) {
     const SolveConsts &c = *w.c;
     const int N = c.N, lane = w.lane, nu = 4 * N;
     double *s = w.s;
     const WarpLayout &L = w.L;
-    const double kappa_eps = c.kappa_eps, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+    const double kappa_eps = c.kappa_eps, kappa_mu = 0.2, tau_min = 0.99;
     const double eta = 1e-4, kappa_sigma = 1e10;
     const double mu_min = c.tol / 10.0;
     double mu = c.mu_init, delta_last = 0.0;
@@ -668,93 +668,85 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
     int status = 1, iter = 0;
     double e_dual = 0.0, e_compl = 0.0;
     for (iter = 0;; ++iter) {
-        double eps = fmax(c.eps_min, c.eps_scale * mu);
-        double f = eval_cost<true, false>(w, eps);
-        // barrier quantities at the current mu
-        double c_mu = 0.0, ec = 0.0;
-        for (int e = lane; e < nu; e += 32) {
-            const int i = e & 3;
-            const double sl = s[L.u + e] - c.lb[i], su = c.ub[i] - s[L.u + e];
-            const double zl = s[L.zl + e], zu = s[L.zu + e];
-            ec = fmax(ec, fmax(sl * zl, su * zu));
-            c_mu = fmax(c_mu, fmax(fabs(sl * zl - mu), fabs(su * zu - mu)));
-            s[L.rdiag + e] = 2.0 * c.wgt[20 + i] + zl / sl + zu / su;
-            s[L.rt + e] = s[L.r + e] - mu / sl + mu / su;
-        }
-        e_compl = warp_max(ec);
-        c_mu = warp_max(c_mu);
-        __syncwarp();
-        double delta = 0.0;
-        int ntry = 0;
-        bool bad = false;
-        for (;;) { // Newton system with inertia correction (IPOPT Algorithm IC schedule)
-            // (the adjoint / dual-infeasibility part of the sweep does not depend on delta)
-            if (riccati_backward(w, delta, &e_dual))
-                break;
-            if (delta == 0.0)
-                delta = (delta_last == 0.0) ? 1e-4 : fmax(1e-20, delta_last / 3.0);
-            else
-                delta *= (delta_last == 0.0) ? 100.0 : 8.0;
-            if (++ntry > 60 || delta > 1e40) {
-                bad = true;
-                break;
-            }
-        }
-        if (bad || !(f == f) || !(e_dual == e_dual)) {
-            status = 3;
-            break;
-        }
-        if (fmax(e_dual, e_compl) <= c.tol) {
-            status = 0;
-            break;
-        }
-        if (iter >= c.max_iter) {
-            status = 1;
-            break;
-        }
-        // monotone barrier update (IPOPT eq. (7)); a change of mu changes the
-        // smoothing and the barrier gradient, so the sweep is redone
-        bool mu_changed = false;
-        while (mu > mu_min && fmax(e_dual, c_mu) <= kappa_eps * mu) {
-            mu = fmax(mu_min, fmin(kappa_mu * mu, pow(mu, theta_mu)));
-            mu_changed = true;
-            double cm = 0.0;
-            for (int e = lane; e < nu; e += 32) {
-                const int i = e & 3;
-                const double sl = s[L.u + e] - c.lb[i], su = c.ub[i] - s[L.u + e];
-                cm = fmax(cm, fmax(fabs(sl * s[L.zl + e] - mu), fabs(su * s[L.zu + e] - mu)));
-            }
-            c_mu = warp_max(cm);
-        }
-        if (mu_changed) {
+        // the warps of a CTA start every iteration together, so that they run the same code
+        // region at the same time and share the instruction cache (the kernel's code is far
+        // larger than it); warps that have finished have exited and no longer count
+        if (SYNC)
+            __syncthreads();
+        double eps = 0.0, f = 0.0, c_mu = 0.0, delta = 0.0;
+        bool stop = false;
+        // pass 0: evaluate, sweep, test convergence, update mu (IPOPT eq. (7)); if mu changed the
+        // smoothing and the barrier gradient changed, so pass 1 evaluates and sweeps again
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
             eps = fmax(c.eps_min, c.eps_scale * mu);
             f = eval_cost<true, false>(w, eps);
+            double ec = 0.0, cm = 0.0;
+#pragma unroll 1
             for (int e = lane; e < nu; e += 32) {
                 const int i = e & 3;
                 const double sl = s[L.u + e] - c.lb[i], su = c.ub[i] - s[L.u + e];
-                s[L.rt + e] = s[L.r + e] - mu / sl + mu / su;
+                const double isl = 1.0 / sl, isu = 1.0 / su;
+                const double zl = s[L.zl + e], zu = s[L.zu + e];
+                ec = fmax(ec, fmax(sl * zl, su * zu));
+                cm = fmax(cm, fmax(fabs(sl * zl - mu), fabs(su * zu - mu)));
+                s[L.rdiag + e] = 2.0 * c.wgt[20 + i] + zl * isl + zu * isu;
+                s[L.rt + e] = s[L.r + e] - mu * isl + mu * isu;
             }
             __syncwarp();
+            // Newton system with inertia correction (IPOPT Algorithm IC schedule); the adjoint /
+            // dual-infeasibility part of the sweep does not depend on delta
             delta = 0.0;
-            ntry = 0;
-            for (;;) {
-                double ed;
-                if (riccati_backward(w, delta, &ed))
-                    break;
+            int ntry = 0;
+            double ed = 0.0;
+#pragma unroll 1
+            while (!riccati_backward(w, delta, &ed)) {
                 if (delta == 0.0)
                     delta = (delta_last == 0.0) ? 1e-4 : fmax(1e-20, delta_last / 3.0);
                 else
                     delta *= (delta_last == 0.0) ? 100.0 : 8.0;
                 if (++ntry > 60 || delta > 1e40) {
-                    bad = true;
+                    status = 3;
+                    stop = true;
                     break;
                 }
             }
-            if (bad) {
-                status = 3;
+            if (stop || pass == 1)
                 break;
+            e_dual = ed;
+            e_compl = warp_max(ec);
+            c_mu = warp_max(cm);
+            if (!(f == f) || !(e_dual == e_dual)) {
+                status = 3;
+                stop = true;
+            } else if (fmax(e_dual, e_compl) <= c.tol) {
+                status = 0;
+                stop = true;
+            } else if (iter >= c.max_iter) {
+                status = 1;
+                stop = true;
             }
+            if (stop)
+                break;
+            bool mu_changed = false;
+#pragma unroll 1
+            while (mu > mu_min && fmax(e_dual, c_mu) <= kappa_eps * mu) {
+                mu = fmax(mu_min, fmin(kappa_mu * mu, mu * sqrt(mu))); // theta_mu = 1.5
+                mu_changed = true;
+                double c2 = 0.0;
+#pragma unroll 1
+                for (int e = lane; e < nu; e += 32) {
+                    const int i = e & 3;
+                    const double sl = s[L.u + e] - c.lb[i], su = c.ub[i] - s[L.u + e];
+                    c2 = fmax(c2, fmax(fabs(sl * s[L.zl + e] - mu), fabs(su * s[L.zu + e] - mu)));
+                }
+                c_mu = warp_max(c2);
+            }
+            if (!mu_changed)
+                break;
         }
+        if (stop)
+            break;
         if (delta > 0.0) {
             delta_last = delta;
             ++n_reg;
@@ -763,13 +755,15 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         const double tau_f = fmax(tau_min, 1.0 - mu);
         // fraction to the boundary (IPOPT eq. (15)), barrier value, slope
         double a_du = 1.0, bar0 = 0.0;
+#pragma unroll 1
         for (int e = lane; e < nu; e += 32) {
             const int i = e & 3;
             const double uu = s[L.u + e], du = s[L.du + e];
             const double sl = uu - c.lb[i], su = c.ub[i] - uu;
             const double zl = s[L.zl + e], zu = s[L.zu + e];
-            const double dzl = mu / sl - zl - zl / sl * du;
-            const double dzu = mu / su - zu + zu / su * du;
+            const double isl = 1.0 / sl, isu = 1.0 / su;
+            const double dzl = mu * isl - zl - zl * isl * du;
+            const double dzu = mu * isu - zu + zu * isu * du;
             if (dzl < 0.0)
                 a_du = fmin(a_du, -tau_f * zl / dzl);
             if (dzu < 0.0)
@@ -786,8 +780,10 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         // become active is reached in one iteration.
         double alpha = 1.0;
         bool accepted = false;
+#pragma unroll 1
         for (int ls = 0; ls < 40; ++ls) {
             double bar = 0.0, gdt = 0.0;
+#pragma unroll 1
             for (int e = lane; e < nu; e += 32) {
                 const int i = e & 3;
                 const double uu = s[L.u + e];
@@ -804,7 +800,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
                 gdt += s[L.q + e] * s[L.dxt + e];
             bar = warp_sum(bar);
             gdt = warp_sum(gdt);
-            const double phit = eval_value<true>(w, eps) - mu * bar;
+            const double phit = eval_value(w, eps, true) - mu * bar;
             if (phit <= phi0 + eta * gdt + 10.0 * 2.220446049250313e-16 * fabs(phi0)) {
                 accepted = true;
                 break;
@@ -821,14 +817,16 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             const double u0 = s[L.u + e], du = s[L.du + e];
             const double sl0 = u0 - c.lb[i], su0 = c.ub[i] - u0;
             double zl = s[L.zl + e], zu = s[L.zu + e];
-            const double dzl = mu / sl0 - zl - zl / sl0 * du;
-            const double dzu = mu / su0 - zu + zu / su0 * du;
+            const double isl0 = 1.0 / sl0, isu0 = 1.0 / su0;
+            const double dzl = mu * isl0 - zl - zl * isl0 * du;
+            const double dzu = mu * isu0 - zu + zu * isu0 * du;
             const double un = u0 + s[L.dut + e];
             const double sl = un - c.lb[i], su = c.ub[i] - un;
+            const double mil = mu / sl, miu = mu / su;
             zl += a_du * dzl;
             zu += a_du * dzu;
-            zl = fmax(fmin(zl, kappa_sigma * mu / sl), mu / (kappa_sigma * sl)); // IPOPT eq. (16)
-            zu = fmax(fmin(zu, kappa_sigma * mu / su), mu / (kappa_sigma * su));
+            zl = fmax(fmin(zl, kappa_sigma * mil), mil * (1.0 / kappa_sigma)); // IPOPT eq. (16)
+            zu = fmax(fmin(zu, kappa_sigma * miu), miu * (1.0 / kappa_sigma));
             s[L.u + e] = un;
             s[L.zl + e] = zl;
             s[L.zu + e] = zu;
@@ -838,7 +836,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         __syncwarp();
     }
     // results: w = [X_0,U_0,...,X_N]; objective without smoothing
-    const double cost = eval_value<false>(w, 0.0);
+    const double cost = eval_value(w, 0.0, false);
     for (int e = lane; e < 10 * (N + 1); e += 32) {
         const int k = e / 10, i = e - 10 * k;
         w_inout[14 * k + i] = s[L.x + e];
@@ -878,7 +876,7 @@ ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double
         return;
     const WarpLayout L(sc->N);
     WarpCtx ctx(sc, wbase + (size_t)warp * L.total, prefix + (size_t)b * sc->n_prefix, lane);
-    solve_instance(ctx, w_inout + (size_t)b * (10 + 14 * sc->N), info + b);
+    solve_instance<(WARPS > 1)>(ctx, w_inout + (size_t)b * (10 + 14 * sc->N), info + b);
 }
 
 } // namespace ampc
