@@ -171,10 +171,10 @@ void refresh_consts(ampc_handle *h) {
 __global__ void repack_kernel(const unsigned char *raw, int64_t scene_stride, int stride,
                               float4 *clouds, const int32_t *counts, int64_t slot_points,
                               int first_scene) {
-    const int scene = first_scene + blockIdx.y;
+    const int scene = first_scene + blockIdx.x; // scenes on x: no 65535 limit
     const int n = counts[scene];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float *p = reinterpret_cast<const float *>(raw + (int64_t)blockIdx.y * scene_stride +
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+        const float *p = reinterpret_cast<const float *>(raw + (int64_t)blockIdx.x * scene_stride +
                                                          (int64_t)i * stride);
         clouds[(int64_t)scene * slot_points + i] = make_float4(p[0], p[1], p[2], 1.0f);
     }
@@ -406,12 +406,14 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
         P.ws_d = h->ws_d.as<double>();
         P.ws_i = h->ws_i.as<uint32_t>();
     }
-    const dim3 grid((Q + KS_WARPS - 1) / KS_WARPS, B, segs);
+    const dim3 grid(B, (Q + KS_WARPS - 1) / KS_WARPS, segs);
+    if (grid.y > 65535u)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "too many queries per instance");
     knn_search_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
     h->launches++;
     CK(cudaGetLastError());
     if (segs > 1) {
-        knn_merge_kernel<<<dim3(grid.x, B), KS_WARPS * 32, 0, st>>>(P);
+        knn_merge_kernel<<<dim3(B, grid.y), KS_WARPS * 32, 0, st>>>(P);
         h->launches++;
         CK(cudaGetLastError());
     }
@@ -430,7 +432,8 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
         CK(cudaFuncSetAttribute(cloud_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KI_BAND_BYTES));
         h->index_smem_set = true;
     }
-    cloud_index_kernel<<<dim3(parts, n_scenes), KI_THREADS, 2 * KI_BAND_BYTES, st>>>(
+    if (parts > 65535) parts = 65535;
+    cloud_index_kernel<<<dim3(n_scenes, parts), KI_THREADS, 2 * KI_BAND_BYTES, st>>>(
         h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
         h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->row_w[kind], first_scene);
     h->launches++;
@@ -724,7 +727,7 @@ static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_sce
                 raw = h->raw_stage.as<unsigned char>();
                 if (n_scenes == 1) scene_stride = (int64_t)per;
             }
-            repack_kernel<<<dim3((maxc + 255) / 256 > 64 ? 64 : (maxc + 255) / 256, n_scenes), 256, 0, st>>>(
+            repack_kernel<<<dim3(n_scenes, (maxc + 255) / 256 > 64 ? 64 : (maxc + 255) / 256), 256, 0, st>>>(
                 raw, scene_stride, stride, slots, h->counts[kind].as<int32_t>(), h->slot_points[kind], first_scene);
             h->launches++;
             CK(cudaGetLastError());

@@ -31,6 +31,7 @@ constexpr int KT_TILE = 64;       // points per tile (2 x 16-byte loads per lane
 constexpr int KNN_KMAX = 32;      // top-k list = one entry per lane
 constexpr int KS_WARPS = 4;       // queries (warps) per search CTA
 constexpr int KS_CHUNK = 1024;    // tile lower bounds kept in shared memory per warp
+constexpr int KS_DENSE = 12;      // candidates in a tile from which the bitonic merge is used
 constexpr int KS_PICKS = 3;       // best-first tile picks before the storage-order sweep
 constexpr int KI_THREADS = 128;   // index kernels: 4 warps per CTA
 
@@ -203,7 +204,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
                  : "memory");
 }
 
-// Index build, common path.  Grid (parts, scenes).  A CTA walks a range of "bands" of its
+// Index build, common path.  Grid (scenes, parts).  A CTA walks a range of "bands" of its
 // scene.  A band is what 32 tiles cover: 8 image rows x up to 256 columns for an organised
 // cloud (8 contiguous row segments), or 2048 consecutive records.  Each band is brought
 // into shared memory by TMA bulk copies (one per row segment, double buffered: the next
@@ -219,7 +220,7 @@ cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes
     extern __shared__ __align__(128) unsigned char ki_smem[];
     __shared__ __align__(8) unsigned long long bar[2];
     float4 *buf[2] = {reinterpret_cast<float4 *>(ki_smem), reinterpret_cast<float4 *>(ki_smem + KI_BAND_BYTES)};
-    const int scene = first_scene + blockIdx.y;
+    const int scene = first_scene + blockIdx.x; // scenes on x: no 65535 limit
     const float4 *c = clouds + (int64_t)scene * slot_points;
     float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
     const int n = counts[scene];
@@ -230,8 +231,8 @@ cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes
     const int segs_x = row_w > 0 ? (row_w + KI_COLS - 1) / KI_COLS : 1;
     const int bands_y = row_w > 0 ? (((n + row_w - 1) / row_w) + 7) / 8 : (n + 8 * KI_COLS - 1) / (8 * KI_COLS);
     const int n_bands = bands_y * segs_x;
-    const int per = (n_bands + gridDim.x - 1) / gridDim.x;
-    const int b_begin = blockIdx.x * per, b_end = min(n_bands, b_begin + per);
+    const int per = (n_bands + gridDim.y - 1) / gridDim.y;
+    const int b_begin = blockIdx.y * per, b_end = min(n_bands, b_begin + per);
     if (b_begin >= b_end)
         return;
     if (tid == 0) {
@@ -395,6 +396,71 @@ __device__ __forceinline__ void topk_insert(TopK &e, int k, double d, uint32_t i
     }
 }
 
+// (dist2, index) lexicographic order
+__device__ __forceinline__ bool topk_less(double ad, uint32_t ai, double bd, uint32_t bi) {
+    return ad < bd || (ad == bd && ai < bi);
+}
+// compare-exchange with the lane `stride` away: keep the smaller (keep_min) or larger element
+__device__ __forceinline__ void cmpx(double &d, uint32_t &i, int stride, bool keep_min) {
+    const double od = __shfl_xor_sync(AMPC_FULL_MASK, d, stride);
+    const uint32_t oi = __shfl_xor_sync(AMPC_FULL_MASK, i, stride);
+    const bool other_less = topk_less(od, oi, d, i);
+    if (other_less == keep_min) {
+        d = od;
+        i = oi;
+    }
+}
+
+// Dense tile (many candidates, k <= 16): bitonic sort of the tile's 64 (dist2, index) pairs
+// (2 per lane: element e = lane + 32 r), then a 32-lane bitonic merge of the 16 best with the
+// list.  ~500 instructions whatever the number of candidates, against ~40 per candidate for
+// the serial insertion; no long dependent chain.
+__device__ __noinline__ void merge_dense_tile(TopK &e, int k, double d0, uint32_t i0, double d1,
+                                              uint32_t i1, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            // both registers hold elements with the same (e & size) for size <= 32
+            const bool asc = (lane & size) == 0;
+            const bool keep_min = ((lane & stride) == 0) == asc;
+            cmpx(d0, i0, stride, keep_min);
+            cmpx(d1, i1, stride, keep_min);
+        }
+    }
+    // size 64: register 1 holds e >= 32 (descending half after the previous stage? no: both
+    // halves are sorted ascending for e&32 == 0 / descending for e&32 != 0 only if the size-32
+    // stage used (e & 32); it used (lane & 32) == 0 for both, so both are ascending: reverse
+    // register 1 to make the 64-sequence bitonic
+    {
+        const double rd = __shfl_sync(AMPC_FULL_MASK, d1, 31 - lane);
+        const uint32_t ri = __shfl_sync(AMPC_FULL_MASK, i1, 31 - lane);
+        d1 = rd;
+        i1 = ri;
+    }
+    if (topk_less(d1, i1, d0, i0)) { // stride 32: within the lane, smaller to register 0
+        const double td = d0;
+        const uint32_t ti = i0;
+        d0 = d1, i0 = i1, d1 = td, i1 = ti;
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1)
+        cmpx(d0, i0, stride, (lane & stride) == 0); // register 0 now holds the 32 smallest, sorted
+    // merge the 16 best of the tile with the list: lanes 0..15 list (ascending, +inf padded),
+    // lanes 16..31 the tile's best 16 reversed -> bitonic; 5 compare-exchange stages sort it
+    double md = __shfl_sync(AMPC_FULL_MASK, d0, 31 - lane);
+    uint32_t mi = __shfl_sync(AMPC_FULL_MASK, i0, 31 - lane);
+    if (lane < 16) {
+        md = e.d;
+        mi = e.i;
+    }
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1)
+        cmpx(md, mi, stride, (lane & stride) == 0);
+    e.d = lane < k ? md : INFINITY;
+    e.i = lane < k ? mi : 0xffffffffu;
+}
+
 // scan one tile: exact distances of its (up to) 64 points, candidates into the list
 __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const TileGeom &g, int tile,
                                           double qx, double qy, double qz, TopK &e, double &kth, int k,
@@ -410,8 +476,15 @@ __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const Tile
         const float4 p = knn_ldg(cloud + i1);
         d1 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
     }
-    unsigned m0 = __ballot_sync(AMPC_FULL_MASK, i0 >= 0 && d0 <= kth);
-    unsigned m1 = __ballot_sync(AMPC_FULL_MASK, i1 >= 0 && d1 <= kth);
+    const bool c0 = i0 >= 0 && d0 <= kth, c1 = i1 >= 0 && d1 <= kth;
+    unsigned m0 = __ballot_sync(AMPC_FULL_MASK, c0);
+    unsigned m1 = __ballot_sync(AMPC_FULL_MASK, c1);
+    if (k <= 16 && __popc(m0) + __popc(m1) >= KS_DENSE) {
+        merge_dense_tile(e, k, c0 ? d0 : INFINITY, c0 ? (uint32_t)i0 : 0xffffffffu, c1 ? d1 : INFINITY,
+                         c1 ? (uint32_t)i1 : 0xffffffffu, lane);
+        kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        return;
+    }
     while (m0) {
         const int src = __ffs(m0) - 1;
         m0 &= m0 - 1;
@@ -509,7 +582,7 @@ knn_search_kernel(const KnnParams P) {
     __shared__ float sLB[KS_WARPS][KS_CHUNK];        // conservative lower bound per tile (NaN = done)
     __shared__ unsigned short sCand[KS_WARPS][KS_CHUNK]; // compacted list of tiles worth visiting
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y, seg = blockIdx.z;
+    const int q = blockIdx.y * KS_WARPS + warp, b = blockIdx.x, seg = blockIdx.z; // b on x: no 65535 limit
     if (q >= P.Q || (P.active && P.active[b] == 0))
         return;
     const int k = P.k;
@@ -616,7 +689,7 @@ knn_search_kernel(const KnnParams P) {
 __global__ void __launch_bounds__(KS_WARPS * 32)
 knn_merge_kernel(const KnnParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int q = blockIdx.x * KS_WARPS + warp, b = blockIdx.y;
+    const int q = blockIdx.y * KS_WARPS + warp, b = blockIdx.x;
     if (q >= P.Q || (P.active && P.active[b] == 0))
         return;
     const int k = P.k;
