@@ -123,3 +123,18 @@ TickResult AvoidanceTick::Step() { // case TASK, :322-355
     r.lastStatus = mMpc.LastStatus();
     return r;
 }
+
+AccelCommand AvoidanceTick::MakeCommand(const TickResult &r, double kp, double kd, double aMaxXy,
+                                        double aMaxZ) const {
+    AccelCommand cmd;
+    if (r.isSafety && r.u.size() >= 3) { // PubCmd
+        cmd.ax = r.u[0], cmd.ay = r.u[1], cmd.az = r.u[2];
+    } else { // PubSlowDownCmd
+        const Eigen::Vector3d accSlow = mVel * (-kp) - mAcc * kd + Eigen::Vector3d(0, 0, 9.8);
+        cmd.ax = std::max(-aMaxXy, std::min(aMaxXy, accSlow.x()));
+        cmd.ay = std::max(-aMaxXy, std::min(aMaxXy, accSlow.y()));
+        cmd.az = std::max(-aMaxZ, std::min(aMaxZ, accSlow.z()));
+    }
+    cmd.yaw = 0;
+    return cmd;
+}

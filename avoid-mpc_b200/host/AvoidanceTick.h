@@ -21,6 +21,15 @@ struct TickParams { // config/mpc_parameters.yaml
     bool useOdomEstimate = true;
 };
 
+// The fields of quadrotor_msgs/Command the planner fills (betaflight_ctrl/quadrotor_msgs/msg/
+// Command.msg:1-17): ACCELERATION_MODE = 1, acceleration xyz, yaw.  ROS-free stand-in for the
+// message published on /bfctrl/cmd (AvoidanceStateMachine.cpp:369-397).
+struct AccelCommand {
+    unsigned char mode = 1; // quadrotor_msgs::Command::ACCELERATION_MODE
+    double ax = 0, ay = 0, az = 0;
+    double yaw = 0;
+};
+
 struct TickResult {
     std::vector<double> u;                       // accel x,y,z + yaw rate (PubCmd input)
     std::vector<std::vector<double>> x0Array;    // predicted [X_i, U_i]
@@ -36,6 +45,10 @@ public:
     void SetOdom(const Eigen::Vector3d &pos, const Eigen::Vector3d &vel, const Eigen::Vector3d &acc,
                  double yaw);
     TickResult Step();
+    // PubCmd (:369-378) when the tick is safe, PubSlowDownCmd (:379-397: PD brake on velocity and
+    // acceleration plus gravity, clamped to the acceleration limits) otherwise
+    AccelCommand MakeCommand(const TickResult &r, double slowDownKp = 0.3, double slowDownKd = 0.3,
+                             double aMaxXy = 10.0, double aMaxZ = 15.0) const;
     const std::vector<std::vector<double>> &RefPath() const { return mRefPath; }
 
 private:

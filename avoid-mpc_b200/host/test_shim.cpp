@@ -2,6 +2,7 @@
 #include "AvoidanceTick.h"
 #include "kd_tree_two.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -71,6 +72,13 @@ int main() {
         CHECK(r.rounds >= 1 && r.u.size() == 4 && r.x0Array.size() == 20 && r.x0Array[0].size() == 14);
         CHECK(r.u[2] >= 5.0 - 1e-9 && r.u[2] <= 15.0 + 1e-9 && std::fabs(r.u[0]) <= 10.0 + 1e-9);
         CHECK(std::isfinite(mpc.LastCost()));
+        const AccelCommand cmd = tick.MakeCommand(r);
+        CHECK(cmd.mode == 1 && cmd.yaw == 0 && cmd.ax == r.u[0] && cmd.az == r.u[2]);
+        TickResult unsafe = r;
+        unsafe.isSafety = false;
+        const AccelCommand brake = tick.MakeCommand(unsafe);
+        CHECK(std::fabs(brake.ax - std::max(-10.0, std::min(10.0, -0.3 * vel.x() - 0.3 * acc.x()))) < 1e-12);
+        CHECK(std::fabs(brake.az - std::max(-15.0, std::min(15.0, -0.3 * vel.z() - 0.3 * acc.z() + 9.8))) < 1e-12);
         std::printf("tick %d rounds %d status %d iters %d cost %.6f u = %.4f %.4f %.4f %.4f\n", t, r.rounds,
                     r.lastStatus, mpc.LastIterations(), mpc.LastCost(), r.u[0], r.u[1], r.u[2], r.u[3]);
         // crude plant: follow the predicted state one control period ahead

@@ -420,6 +420,46 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_cpu_c0(args):
+    """BASELINE config C0 (the reference's own CPU-runnable case): single instance, N=20, K=8,
+    10 000-point cloud, ONE thread; p50/p90 of tree build, 20x8-NN, NLP solve and total."""
+    import avoid_mpc_b200 as A
+    from oracle import oracle as O
+    D, S = A.defaults, A.synth
+    K, npts, n_inst = 8, 10000, max(50, args.steps * 50)
+    use_ref = O.ref_available()
+    lb, ub = D.u_bounds()
+    opts = O.default_opts()
+    t_build, t_knn, t_solve, iters, conv = [], [], [], [], 0
+    scenes = [(S.forest_cloud(20_000 + s, npts)[0], S.states(20_000 + s, N_H)) for s in range(min(n_inst, 64))]
+    for i in range(n_inst):
+        c, (x0, ref, tgt) = scenes[i % len(scenes)]
+        t0 = time.perf_counter()
+        tree = O.RefTree(c) if use_ref else O.PortTree(c)
+        t1 = time.perf_counter()
+        idx, d2, cnt = tree.search(ref[:, :3], K)
+        t2 = time.perf_counter()
+        ob = c[idx.reshape(-1), :3].astype(np.float64).reshape(N_H, K, 3)
+        p = S.full_params(S.pack_prefix(x0, ref, ob, tgt))
+        w0 = S.warm_start(args.warm, x0, ref, N_H)
+        t3 = time.perf_counter()
+        w, info = O.solve(N_H, K, DT, p, w0, lb, ub, opts)
+        t4 = time.perf_counter()
+        t_build.append(t1 - t0), t_knn.append(t2 - t1), t_solve.append(t4 - t3)
+        iters.append(info.iters)
+        conv += info.status == 0
+    tot = [a + b + c_ for a, b, c_ in zip(t_build, t_knn, t_solve)]
+    q = lambda v, p_: float(np.percentile(np.array(v) * 1e3, p_))
+    print(json.dumps({"mode": "cpu_c0", "config": "single instance, N=20, K=8, 10000-pt cloud, 1 thread",
+                      "instances": n_inst, "knn_impl": "reference nanoflann (oracle/_ref)" if use_ref else "C restatement",
+                      "nlp_impl": "oracle interior-point port (tol 1e-8)", "unit": "ms",
+                      "tree_build": {"p50": q(t_build, 50), "p90": q(t_build, 90)},
+                      "knn_20x8": {"p50": q(t_knn, 50), "p90": q(t_knn, 90)},
+                      "nlp_solve": {"p50": q(t_solve, 50), "p90": q(t_solve, 90)},
+                      "total": {"p50": q(tot, 50), "p90": q(tot, 90)},
+                      "iters_p50": float(np.median(iters)), "converged_frac": conv / n_inst}), flush=True)
+
+
 def run_knn_sweep(args):
     """BASELINE config C4: k-NN only, cloud sizes 10k..1M points, Q=20, K=16, ~2 GB of clouds per
     GPU; achieved GB/s of the k-NN stage (index build + search) against the measured HBM peak."""
@@ -486,13 +526,15 @@ def main():
     ap.add_argument("--max-iter", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unorganised", action="store_true", help="do not pass the image row pitch to the index")
-    ap.add_argument("--mode", default="solves", choices=["solves", "knn_sweep"])
+    ap.add_argument("--mode", default="solves", choices=["solves", "knn_sweep", "cpu_c0"])
     ap.add_argument("--streams", type=int, default=4, help="independent batches in flight per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.mode == "knn_sweep":
         run_knn_sweep(args)
+    elif args.mode == "cpu_c0":
+        run_cpu_c0(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:
