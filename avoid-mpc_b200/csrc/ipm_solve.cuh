@@ -12,18 +12,20 @@
 //   l_k = path quadratic in the yaw-rotated error + sum_j lambda*softplus(-32(r-R))*|v.n|
 //   (k < N-1),  terminal quadratic (k = N-1).
 //
-// Method (see DESIGN.md "Solver"): primal-dual log-barrier on the control box
-// with IPOPT's monotone mu rule, fraction-to-the-boundary rule, inertia-correction
-// schedule and multiplier safeguard; iterates stay on the dynamics manifold
-// (X = roll-out of U), the Newton system of the multiple-shooting NLP is solved
-// exactly by a stage-wise Riccati sweep (nx = 10, nu = 4) exploiting the chain
-// sparsity of Phi/Gam; Armijo backtracking on the barrier objective.  |v.n| is
-// smoothed inside the solver as sqrt(s^2+eps^2)-eps with eps = max(eps_min, mu).
+// Method (see DESIGN.md "Solver"): primal-dual log-barrier on the control box with
+// IPOPT's monotone mu rule, fraction-to-the-boundary rule, inertia-correction schedule and
+// multiplier safeguard; iterates stay on the dynamics manifold (X = roll-out of U); the
+// Newton system of the multiple-shooting NLP is solved exactly by a stage-wise Riccati
+// sweep; projected Armijo line search on the barrier objective.  |v.n| is smoothed inside
+// the solver as sqrt(s^2+eps^2)-eps with eps = max(eps_min, mu).
 //
-// Lane mapping.  Cost/gradient/Hessian evaluation: lane = stage (all N stages
-// in parallel, K obstacle terms accumulated in registers, no reduction except
-// the objective value).  Riccati sweep: the 32 lanes share the entries of the
-// 10x10 / 10x4 / 4x4 stage matrices, which live in warp-private shared memory.
+// Lane mapping.  Cost/gradient/Hessian evaluation: lane = stage (all N stages in parallel,
+// the K obstacle terms accumulated in registers).  Value-only evaluation (line-search
+// trials): collision terms spread over all 32 lanes.  Riccati sweep: the dynamics split
+// into four chains (x, y, z axis: p,v,a; yaw); lane 4i+j owns the 3x3 block P^(ij) coupling
+// chain i and chain j IN REGISTERS, S = R + G'PG is gathered by shuffles and factored as
+// LDL' redundantly; no matrix lives in shared memory.  Warp-private shared memory holds the
+// iterate, the step, gradients, compact (p,v) Hessian blocks and the feedback gains.
 #pragma once
 #include "common.cuh"
 

@@ -6,22 +6,24 @@
 // queries per launch.
 //
 // Index ("build", once per cloud = once per depth frame, src/FrameKDMap.cpp:34-52):
-//   ONE coalesced streaming pass over the 16-byte point records drops the points
-//   whose x is NaN (order preserving, kd_tree_two.h:99-101) and emits the bounding
-//   box of every run of 64 consecutive points (32 B per tile, 3% of the cloud).
-//   Depth-image clouds are stored in raster order, so a run of 64 points is a short
-//   piece of one image row: a thin, tight box.  This pass is the HBM-bound kernel
-//   of the k-NN stage; nothing is sorted and no hierarchy is built.
-// Search: one warp per (instance, query).  Lanes evaluate the exact lower bound of
-//   the query to 32 tile boxes at a time; the nearest tile is scanned first to get a
-//   finite k-th-best bound, then only tiles whose lower bound does not exceed the
-//   current bound are read.  The top-k list lives in registers (lane j = entry j).
+//   ONE streaming pass over the 16-byte point records (TMA bulk copies into double-
+//   buffered shared memory) emits, per tile of 64 points, the bounding box and the number
+//   of points inside (32 B per tile, 3% of the cloud).  A tile is 64 consecutive records,
+//   or an 8x8 patch of the depth image when the row pitch is known (organised cloud).
+//   Records whose x is NaN (kd_tree_two.h:99-101) raise a flag; a second, normally idle
+//   kernel compacts such scenes in place (order preserving) and rebuilds their boxes.
+//   This pass is the HBM-bound kernel of the k-NN stage; nothing is sorted.
+// Search: one warp per (instance, query).  Lanes evaluate conservative FP32 lower / upper
+//   bounds of the query to 32 tile boxes at a time; a few best-first picks give a tight
+//   k-th-best bound, then only tiles whose lower bound does not exceed the current bound
+//   are read.  The top-k list lives in registers (lane j = entry j); dense tiles are merged
+//   with a warp bitonic network.
 //
-// Arithmetic is the reference's, operation for operation: dist2 = ((dx*dx + dy*dy)
-// + dz*dz) in double from float coordinates, each operation rounded separately
-// (nanoflann_two.hpp:590-599, kd_tree_two.h:34-41); box lower bounds use the same
-// operations in the same order, so rounding can never prune a true neighbour.
-// Indices AND squared distances are bit-exact; order is canonical (dist2, index).
+// Arithmetic of the distances is the reference's, operation for operation: dist2 =
+// ((dx*dx + dy*dy) + dz*dz) in double from float coordinates, each operation rounded
+// separately (nanoflann_two.hpp:590-599, kd_tree_two.h:34-41).  The pruning bounds are
+// rounded toward the safe side, so rounding can never prune a true neighbour.  Indices
+// AND squared distances are bit-exact; order is canonical (dist2, index).
 #pragma once
 #include "common.cuh"
 
@@ -115,18 +117,6 @@ __device__ __forceinline__ double knn_dist2(double qx, double qy, double qz, flo
     r = __dadd_rn(r, __dmul_rn(d1, d1));
     const double d2 = __dsub_rn(qz, (double)pz);
     r = __dadd_rn(r, __dmul_rn(d2, d2));
-    return r;
-}
-
-// Lower bound of knn_dist2 over every point inside the box (monotone rounding).
-__device__ __forceinline__ double knn_box_lb(double qx, double qy, double qz, float lx, float ly,
-                                             float lz, float hx, float hy, float hz) {
-    const double ax = fmax(fmax(__dsub_rn((double)lx, qx), __dsub_rn(qx, (double)hx)), 0.0);
-    double r = __dmul_rn(ax, ax);
-    const double ay = fmax(fmax(__dsub_rn((double)ly, qy), __dsub_rn(qy, (double)hy)), 0.0);
-    r = __dadd_rn(r, __dmul_rn(ay, ay));
-    const double az = fmax(fmax(__dsub_rn((double)lz, qz), __dsub_rn(qz, (double)hz)), 0.0);
-    r = __dadd_rn(r, __dmul_rn(az, az));
     return r;
 }
 
@@ -428,10 +418,8 @@ __device__ __noinline__ void merge_dense_tile(TopK &e, int k, double d0, uint32_
             cmpx(d1, i1, stride, keep_min);
         }
     }
-    // size 64: register 1 holds e >= 32 (descending half after the previous stage? no: both
-    // halves are sorted ascending for e&32 == 0 / descending for e&32 != 0 only if the size-32
-    // stage used (e & 32); it used (lane & 32) == 0 for both, so both are ascending: reverse
-    // register 1 to make the 64-sequence bitonic
+    // both registers are now sorted ascending across the lanes; reversing register 1 makes the
+    // 64-element sequence (register 0, then register 1) bitonic for the final merge
     {
         const double rd = __shfl_sync(AMPC_FULL_MASK, d1, 31 - lane);
         const uint32_t ri = __shfl_sync(AMPC_FULL_MASK, i1, 31 - lane);
@@ -563,18 +551,6 @@ __device__ __forceinline__ float knn_box_ub32(const QueryF &q, float lx, float l
     const float az = fmaxf(fabsf(__fsub_ru(q.zhi, lz)), fabsf(__fsub_rd(q.zlo, hz)));
     const float r = __fadd_ru(__fadd_ru(__fmul_ru(ax, ax), __fmul_ru(ay, ay)), __fmul_ru(az, az));
     return __fmul_ru(r, 1.00000095367431640625f); // 1 + 2^-20
-}
-
-// Upper bound of knn_dist2 over every point inside the box (farthest corner).
-__device__ __forceinline__ double knn_box_ub(double qx, double qy, double qz, float lx, float ly,
-                                             float lz, float hx, float hy, float hz) {
-    const double ax = fmax(fabs(__dsub_rn(qx, (double)lx)), fabs(__dsub_rn(qx, (double)hx)));
-    double r = __dmul_rn(ax, ax);
-    const double ay = fmax(fabs(__dsub_rn(qy, (double)ly)), fabs(__dsub_rn(qy, (double)hy)));
-    r = __dadd_rn(r, __dmul_rn(ay, ay));
-    const double az = fmax(fabs(__dsub_rn(qz, (double)lz)), fabs(__dsub_rn(qz, (double)hz)));
-    r = __dadd_rn(r, __dmul_rn(az, az));
-    return r;
 }
 
 __global__ void __launch_bounds__(KS_WARPS * 32, 6)
