@@ -785,6 +785,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
 #pragma unroll 1
         for (int ls = 0; ls < 40; ++ls) {
             double bar = 0.0, gdt = 0.0;
+            __syncwarp(); // the previous trial's reads of dut / dxt are complete
 #pragma unroll 1
             for (int e = lane; e < nu; e += 32) {
                 const int i = e & 3;

@@ -629,6 +629,7 @@ knn_search_kernel(const KnnParams P) {
             double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
             scan_tile(cloud, n, g, c0 + j, qx, qy, qz, e, kth, k, lane);
             bound = fmin(bound, kth);
+            __syncwarp(); // every lane has finished reading lbuf for this pick
             if (lane == 0)
                 lbuf[j] = NAN;
             __syncwarp();
