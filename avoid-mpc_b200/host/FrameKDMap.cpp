@@ -1,5 +1,6 @@
 #include "FrameKDMap.h"
 
+#include <algorithm>
 #include <cmath>
 #include <limits>
 #include <stdexcept>
@@ -9,13 +10,36 @@ namespace {
 [[noreturn]] void die(ampc_handle *h, const char *what) {
     throw std::runtime_error(std::string("FrameKDMap(GPU): ") + what + ": " + ampc_last_error(h));
 }
+Mat4 mul(const Mat4 &a, const Mat4 &b) {
+    Mat4 c{};
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int l = 0; l < 4; ++l)
+                s += a[4 * i + l] * b[4 * l + j];
+            c[4 * i + j] = s;
+        }
+    return c;
+}
+Mat4 rigid_inverse(const Mat4 &T) { // [R t; 0 1]^-1 = [R' -R't; 0 1]
+    Mat4 I{};
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            I[4 * i + j] = T[4 * j + i];
+        I[4 * i + 3] = -(T[0 + i] * T[3] + T[4 + i] * T[7] + T[8 + i] * T[11]);
+    }
+    I[15] = 1;
+    return I;
+}
 } // namespace
 
-FrameKDMap::FrameKDMap(int maxPoints, int maxEdgePoints) {
+Mat4 Mat4Identity() { return {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; }
+
+FrameKDMap::FrameKDMap(int maxPoints, int maxEdgePoints, const MapParams &p) : mP(p) {
     ampc_config cfg{};
     cfg.N = 1, cfg.K = 1, cfg.dt = 1.0;
-    cfg.max_batch = 64; // query sites per QueryNearestBatch call
-    cfg.max_scenes = 1;
+    cfg.max_batch = std::max(64, p.maxFrameCount + 2);
+    cfg.max_scenes = p.maxFrameCount + 2; // slot 0 = current frame, the rest = key-frames
     cfg.max_points = maxPoints;
     cfg.max_edge_points = maxEdgePoints;
     cfg.device = 0;
@@ -23,18 +47,88 @@ FrameKDMap::FrameKDMap(int maxPoints, int maxEdgePoints) {
     if (ampc_create(&cfg, &h) != AMPC_OK)
         die(nullptr, "ampc_create");
     mHandle.reset(h, ampc_destroy);
+    for (int s = cfg.max_scenes - 1; s >= 1; --s)
+        mFreeSlots.push_back(s);
+    mCur.slot = 0;
+    mCur.Twc = Mat4Identity();
 }
 
-void FrameKDMap::AddClouds(const CloudPtr &cloud, const CloudPtr &edgeCloud) {
-    const CloudPtr *src[2] = {&cloud, &edgeCloud};
+void FrameKDMap::Upload(Frame &f) {
+    const std::vector<pcl::PointXYZ> *src[2] = {&f.pts, &f.edge};
     for (int kind = 0; kind < 2; ++kind) {
-        const auto &pts = (*src[kind])->points;
-        if (ampc_cloud_set(mHandle.get(), 0, kind, pts.data(), (int)pts.size(), 16) != AMPC_OK)
+        if (ampc_cloud_set(mHandle.get(), f.slot, kind, src[kind]->data(), (int)src[kind]->size(), 16) != AMPC_OK)
             die(mHandle.get(), "ampc_cloud_set");
         int32_t n = 0;
-        if (ampc_cloud_count(mHandle.get(), 0, kind, &n) != AMPC_OK)
+        if (ampc_cloud_count(mHandle.get(), f.slot, kind, &n) != AMPC_OK)
             die(mHandle.get(), "ampc_cloud_count");
-        mCount[kind] = n; // after the NaN filter of KDTreeTwo::Initialize (kd_tree_two.h:99-101)
+        f.count[kind] = n; // after the NaN filter of KDTreeTwo::Initialize (kd_tree_two.h:99-101)
+    }
+}
+
+void FrameKDMap::AddClouds(const CloudPtr &cloud, const CloudPtr &edgeCloud, const Mat4 &Twc, int rowWidthHint) {
+    if (ampc_cloud_set_layout(mHandle.get(), AMPC_CLOUD_OBSTACLE, rowWidthHint) != AMPC_OK)
+        die(mHandle.get(), "ampc_cloud_set_layout");
+    mCur.pts.clear();
+    for (const auto &p : cloud->points) // keep the host copy NaN-filtered like the tree's own copy
+        if (!(p.x != p.x))
+            mCur.pts.push_back(p);
+    mCur.edge.clear();
+    for (const auto &p : edgeCloud->points)
+        if (!(p.x != p.x))
+            mCur.edge.push_back(p);
+    mCur.Twc = Twc;
+    Upload(mCur);
+    mHaveCur = true;
+}
+
+bool FrameKDMap::PtIsInFrame(const Eigen::Vector3d &ptw, const Mat4 &Twc) const { // :215-231
+    const Mat4 Tcw = rigid_inverse(Twc);
+    const double x = Tcw[0] * ptw.x() + Tcw[1] * ptw.y() + Tcw[2] * ptw.z() + Tcw[3];
+    const double y = Tcw[4] * ptw.x() + Tcw[5] * ptw.y() + Tcw[6] * ptw.z() + Tcw[7];
+    const double z = Tcw[8] * ptw.x() + Tcw[9] * ptw.y() + Tcw[10] * ptw.z() + Tcw[11];
+    if (z > mP.depthMax || z < 0)
+        return false;
+    const double u = mP.fx * x / z + mP.cx, v = mP.fy * y / z + mP.cy;
+    return !(u < 0 || u >= mP.width || v < 0 || v >= mP.height);
+}
+
+std::vector<const FrameKDMap::Frame *> FrameKDMap::QueryVector() const { // :65-75
+    std::vector<const Frame *> v;
+    if (mHaveCur)
+        v.push_back(&mCur);
+    for (size_t i = 0; i + 1 < mKeyFrames.size(); ++i) // all key-frames but the last
+        v.push_back(&mKeyFrames[i]);
+    return v;
+}
+
+// one batched launch: instance f = frame f, the same query for every frame.  Frames follow the
+// reference's per-frame rule (:293-297 + kd_tree_two.h:117-124): queryPointCount = min(k, n), and
+// SearchForNearest returns nothing when n == queryPointCount, i.e. only frames with n > k answer.
+void FrameKDMap::SearchFrames(const std::vector<const Frame *> &frames, const Eigen::Vector3d &p, int k,
+                              int kind, std::vector<std::vector<Eigen::Vector3d>> &pts,
+                              std::vector<std::vector<double>> &d2) {
+    const int F = (int)frames.size();
+    pts.assign(F, {});
+    d2.assign(F, {});
+    if (F == 0 || k <= 0)
+        return;
+    std::vector<int32_t> scene_of(F), cnt(F);
+    std::vector<double> q(3 * F), dd((size_t)F * k), pp((size_t)F * k * 3);
+    for (int f = 0; f < F; ++f) {
+        scene_of[f] = frames[f]->slot;
+        q[3 * f] = p.x(), q[3 * f + 1] = p.y(), q[3 * f + 2] = p.z();
+    }
+    if (ampc_knn_batch(mHandle.get(), kind, F, scene_of.data(), q.data(), 1, k, nullptr, dd.data(), pp.data(),
+                       cnt.data()) != AMPC_OK)
+        die(mHandle.get(), "ampc_knn_batch");
+    for (int f = 0; f < F; ++f) {
+        if (frames[f]->count[kind] <= k)
+            continue; // n < k asks for n and gets none; n == k gets none
+        for (int j = 0; j < cnt[f]; ++j) {
+            const double *c = &pp[((size_t)f * k + j) * 3];
+            pts[f].emplace_back(c[0], c[1], c[2]);
+            d2[f].push_back(dd[(size_t)f * k + j]);
+        }
     }
 }
 
@@ -45,19 +139,17 @@ void FrameKDMap::QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, i
     out.assign(Q, {});
     distances.assign(Q, {});
     const int kind = queryEdge ? AMPC_CLOUD_EDGE : AMPC_CLOUD_OBSTACLE;
-    const int n = mCount[kind];
+    const int n = mCur.count[kind];
     if (Q == 0 || n == 0 || k <= 0)
         return;
-    // FrameKDMap.cpp:339-345 / :293-297: ask for min(k, n) neighbours; SearchForNearest then
-    // returns nothing when the cloud holds exactly that many points (kd_tree_two.h:117-124)
     const int kq = k < n ? k : n;
     std::vector<double> q(3 * Q), d2((size_t)Q * kq), pts((size_t)Q * kq * 3);
     std::vector<int32_t> cnt(Q);
     for (int i = 0; i < Q; ++i)
         q[3 * i] = points[i].x(), q[3 * i + 1] = points[i].y(), q[3 * i + 2] = points[i].z();
-    // one instance (scene 0), Q queries
-    if (ampc_knn_batch(mHandle.get(), kind, 1, nullptr, q.data(), Q, kq, nullptr, d2.data(),
-                       pts.data(), cnt.data()) != AMPC_OK)
+    const int32_t scene0 = mCur.slot;
+    if (ampc_knn_batch(mHandle.get(), kind, 1, &scene0, q.data(), Q, kq, nullptr, d2.data(), pts.data(),
+                       cnt.data()) != AMPC_OK)
         die(mHandle.get(), "ampc_knn_batch");
     for (int i = 0; i < Q; ++i)
         for (int j = 0; j < cnt[i]; ++j) {
@@ -67,25 +159,132 @@ void FrameKDMap::QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, i
         }
 }
 
-void FrameKDMap::QueryNearest(const Eigen::Vector3d &point, int nearestPointCount,
-                              std::vector<Eigen::Vector3d> &out, std::vector<double> &distances,
-                              bool queryEdge) {
-    std::vector<std::vector<Eigen::Vector3d>> o;
-    std::vector<std::vector<double>> d;
-    QueryNearestBatch({point}, nearestPointCount, o, d, queryEdge);
-    out = o.empty() ? std::vector<Eigen::Vector3d>() : o[0];
-    distances = d.empty() ? std::vector<double>() : d[0];
+void FrameKDMap::QueryNearest(const Eigen::Vector3d &point, int k, std::vector<Eigen::Vector3d> &out,
+                              std::vector<double> &distances, bool queryEdge) {
+    out.clear();
+    distances.clear();
+    const int kind = queryEdge ? AMPC_CLOUD_EDGE : AMPC_CLOUD_OBSTACLE;
+    // fast path (:329-346): the current frame alone
+    if (mHaveCur && mCur.count[kind] >= k && PtIsInFrame(point, mCur.Twc)) {
+        std::vector<std::vector<Eigen::Vector3d>> o;
+        std::vector<std::vector<double>> d;
+        QueryNearestBatch({point}, k, o, d, queryEdge);
+        out = o[0];
+        distances = d[0];
+        return;
+    }
+    // slow path (:347-375): every frame of the query vector, merge, sort by distance, keep k
+    std::vector<std::vector<Eigen::Vector3d>> pts;
+    std::vector<std::vector<double>> d2;
+    SearchFrames(QueryVector(), point, k, kind, pts, d2);
+    std::vector<std::pair<double, Eigen::Vector3d>> all;
+    for (size_t f = 0; f < pts.size(); ++f)
+        for (size_t j = 0; j < pts[f].size(); ++j)
+            all.emplace_back(d2[f][j], pts[f][j]);
+    std::stable_sort(all.begin(), all.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+    for (int i = 0; i < k && i < (int)all.size(); ++i) {
+        out.push_back(all[i].second);
+        distances.push_back(all[i].first);
+    }
 }
 
-double FrameKDMap::GetNearestDistance(const Eigen::Vector3d &point) {
-    // FrameKDMap.cpp:400-427: sqrt of the smallest squared 1-NN distance over the frames
+double FrameKDMap::GetNearestDistance(const Eigen::Vector3d &point) { // :400-427
     double nearest = std::numeric_limits<double>::max();
-    if (mCount[0] == 0)
-        return nearest; // empty map: returned un-rooted (:402-404)
-    std::vector<Eigen::Vector3d> o;
-    std::vector<double> d;
-    QueryNearest(point, 1, o, d, false);
-    if (!d.empty())
-        nearest = d[0];
+    const std::vector<const Frame *> all = QueryVector();
+    if (all.empty())
+        return nearest; // returned un-rooted (:402-404)
+    std::vector<const Frame *> frames;
+    for (const Frame *f : all)
+        if (f->count[0] > 0) // frames with an empty Obstacle cloud are skipped (:383-386)
+            frames.push_back(f);
+    std::vector<std::vector<Eigen::Vector3d>> pts;
+    std::vector<std::vector<double>> d2;
+    SearchFrames(frames, point, 1, AMPC_CLOUD_OBSTACLE, pts, d2);
+    for (const auto &d : d2)
+        if (!d.empty())
+            nearest = std::min(nearest, d[0]);
     return std::sqrt(nearest);
+}
+
+bool FrameKDMap::DroneBehindPts(const Mat4 &Twc, const Frame &frame) { // :233-252
+    const Mat4 Twb = mul(Twc, rigid_inverse(mP.Tbc));
+    const Eigen::Vector3d twb(Twb[3], Twb[7], Twb[11]);
+    const int ptsCount = std::min(frame.count[0], 10);
+    std::vector<std::vector<Eigen::Vector3d>> pts;
+    std::vector<std::vector<double>> d2;
+    if (ptsCount > 0) {
+        // SearchForNearest(twb, ptsCount) on that frame: nothing when the frame holds exactly ptsCount points
+        std::vector<int32_t> cnt(1);
+        std::vector<double> q = {twb.x(), twb.y(), twb.z()}, dd(ptsCount), pp(3 * (size_t)ptsCount);
+        const int32_t slot = frame.slot;
+        if (ampc_knn_batch(mHandle.get(), AMPC_CLOUD_OBSTACLE, 1, &slot, q.data(), 1, ptsCount, nullptr, dd.data(),
+                           pp.data(), cnt.data()) != AMPC_OK)
+            die(mHandle.get(), "ampc_knn_batch");
+        for (int j = 0; j < cnt[0]; ++j) {
+            // ptb = Rbw (ptw - twb); only its x component matters
+            const double dx = pp[3 * j] - twb.x(), dy = pp[3 * j + 1] - twb.y(), dz = pp[3 * j + 2] - twb.z();
+            const double ptb_x = Twb[0] * dx + Twb[4] * dy + Twb[8] * dz; // first row of Rwb' = first column of Rwb
+            if (ptb_x <= mP.depthMin)
+                return false;
+        }
+    }
+    return true;
+}
+
+void FrameKDMap::InsertKeyFrame() { // :428-432: the key-frame is the current frame's snapshot
+    if (!mHaveCur)
+        return;
+    if (mFreeSlots.empty())
+        RemoveOldVertex();
+    Frame f = mCur;
+    f.slot = mFreeSlots.back();
+    mFreeSlots.pop_back();
+    Upload(f);
+    mKeyFrames.push_back(std::move(f));
+}
+
+void FrameKDMap::RemoveOldVertex() { // :59-63
+    if (mKeyFrames.empty())
+        return;
+    mFreeSlots.push_back(mKeyFrames.front().slot);
+    mKeyFrames.pop_front();
+}
+
+void FrameKDMap::ProcessKeyframes() { // body of KeyframeThreadWorker, :446-487
+    if (!mHaveCur)
+        return;
+    if (mKeyFrames.empty()) {
+        InsertKeyFrame();
+        return;
+    }
+    while (!mKeyFrames.empty()) {
+        if ((int)mKeyFrames.size() > mP.maxFrameCount || !DroneBehindPts(mCur.Twc, mKeyFrames.front()))
+            RemoveOldVertex();
+        else
+            break;
+    }
+    if (mKeyFrames.empty())
+        return;
+    // points of the last key-frame farther than keyframe_th_dist from the current cloud
+    Frame &last = mKeyFrames.back();
+    const int n = (int)last.pts.size();
+    std::vector<pcl::PointXYZ> outliers;
+    if (n > 0 && mCur.count[0] > 0) {
+        std::vector<double> q(3 * (size_t)n), d2(n);
+        std::vector<int32_t> cnt(n);
+        for (int i = 0; i < n; ++i)
+            q[3 * i] = last.pts[i].x, q[3 * i + 1] = last.pts[i].y, q[3 * i + 2] = last.pts[i].z;
+        const int32_t slot = mCur.slot;
+        if (ampc_knn_batch(mHandle.get(), AMPC_CLOUD_OBSTACLE, 1, &slot, q.data(), n, 1, nullptr, d2.data(), nullptr,
+                           cnt.data()) != AMPC_OK)
+            die(mHandle.get(), "ampc_knn_batch");
+        for (int i = 0; i < n; ++i)
+            if (cnt[i] > 0 && std::sqrt(d2[i]) > mP.keyframeDistanceTh)
+                outliers.push_back(last.pts[i]);
+    }
+    if ((int)outliers.size() < mP.keyframeCountTh)
+        return;
+    last.pts = outliers; // lastPtCloudPtr->InitializeNew(newCloud), :484
+    Upload(last);
+    InsertKeyFrame();
 }

@@ -86,6 +86,79 @@ int main() {
         vel = Eigen::Vector3d(r.x0Array[1][4], r.x0Array[1][5], r.x0Array[1][6]);
         acc = Eigen::Vector3d(r.x0Array[1][7], r.x0Array[1][8], r.x0Array[1][9]);
     }
+
+    // ---- FrameKDMap with key-frames: slow path of QueryNearest / GetNearestDistance (FrameKDMap.cpp:347-427)
+    {
+        MapParams mp;
+        mp.maxFrameCount = 4;
+        FrameKDMap kmap(8192, 1024, mp);
+        auto mat = [](double x, double y, double z) { // Twc = Twb(t = xyz, R = I) * Tbc
+            Mat4 T = MapParams().Tbc;
+            T[3] += x, T[7] += y, T[11] += z;
+            return T;
+        };
+        std::vector<std::shared_ptr<pcl::PointCloud<pcl::PointXYZ>>> cl(4);
+        auto none = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+        for (int f = 0; f < 4; ++f) {
+            cl[f] = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+            for (int i = 0; i < 3000; ++i)
+                cl[f]->points.emplace_back(ux(rng) + 5.f * f, uy(rng), uz(rng));
+            kmap.AddClouds(cl[f], none, mat(-50, 0, 1.5));
+            if (f < 3) kmap.InsertKeyFrame();
+        }
+        CHECK(kmap.KeyFrameCount() == 3 && kmap.PointCount(false) == 3000 && kmap.KeyFramePointCount(2) == 3000);
+        // query vector = current (cl[3]) + key-frames 0 and 1; the last key-frame (cl[2]) is left out (:65-75)
+        auto brute = [&](const Eigen::Vector3d &q, std::vector<int> frames) {
+            std::vector<double> d;
+            for (int f : frames)
+                for (const auto &p : cl[f]->points) {
+                    const double d0 = q.x() - p.x, d1 = q.y() - p.y, d2 = q.z() - p.z;
+                    d.push_back((d0 * d0 + d1 * d1) + d2 * d2);
+                }
+            std::sort(d.begin(), d.end());
+            return d;
+        };
+        std::vector<Eigen::Vector3d> out;
+        std::vector<double> dist;
+        const Eigen::Vector3d behind(-60, 0.3, 1.2), ahead(12, 0.2, 1.4);
+        CHECK(!kmap.PtIsInFrame(behind, mat(-50, 0, 1.5)) && kmap.PtIsInFrame(ahead, mat(-50, 0, 1.5)));
+        kmap.QueryNearest(behind, 8, out, dist);
+        std::vector<double> want = brute(behind, {3, 0, 1});
+        CHECK(out.size() == 8 && dist.size() == 8);
+        for (int j = 0; j < 8; ++j) CHECK(dist[j] == want[j]);
+        const Eigen::Vector3d side(12, 100, 1.4); // out of the frustum sideways
+        kmap.QueryNearest(side, 16, out, dist);
+        want = brute(side, {3, 0, 1});
+        CHECK(dist.size() == 16);
+        for (int j = 0; j < 16; ++j) CHECK(dist[j] == want[j]);
+        kmap.QueryNearest(ahead, 8, out, dist); // fast path: current frame only
+        want = brute(ahead, {3});
+        for (int j = 0; j < 8; ++j) CHECK(dist[j] == want[j]);
+        CHECK(kmap.GetNearestDistance(ahead) == std::sqrt(brute(ahead, {3, 0, 1})[0]));
+        // ProcessKeyframes: the last key-frame keeps only its points farther than 0.1 m from the
+        // current cloud, then the current frame becomes a key-frame (:462-486)
+        auto cur = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+        for (int i = 0; i < 1500; ++i) cur->points.push_back(cl[2]->points[i]);
+        for (int i = 0; i < 1500; ++i) cur->points.emplace_back(ux(rng) + 40.f, uy(rng), uz(rng));
+        kmap.AddClouds(cur, none, mat(-50, 0, 1.5));
+        int expect = 0;
+        for (const auto &p : cl[2]->points) {
+            double best = 1e300;
+            for (const auto &c : cur->points) {
+                const double d0 = (double)p.x - c.x, d1 = (double)p.y - c.y, d2 = (double)p.z - c.z;
+                best = std::min(best, (d0 * d0 + d1 * d1) + d2 * d2);
+            }
+            if (std::sqrt(best) > 0.1) ++expect;
+        }
+        CHECK(expect >= 10 && expect <= 1500);
+        kmap.ProcessKeyframes();
+        CHECK(kmap.KeyFrameCount() == 4 && kmap.KeyFramePointCount(2) == expect && kmap.KeyFramePointCount(3) == 3000);
+        // a frame the drone has flown past is dropped (DroneBehindPts, :233-252; prune loop :451-458)
+        kmap.AddClouds(cur, none, mat(9, 0, 1.5));
+        kmap.ProcessKeyframes();
+        CHECK(kmap.KeyFrameCount() < 4);
+        std::printf("keyframes ok: outliers kept %d, frames now %d\n", expect, kmap.KeyFrameCount());
+    }
     std::printf("SHIM_OK\n");
     return 0;
 }
