@@ -41,7 +41,7 @@ def scene_params(scene_id: int):
     return rng, cx, cy, cr
 
 
-def _depth_image(W, H, cx, cy, cr, origin):
+def _depth_image(W, H, cx, cy, cr, origin, back_wall=40.0):
     """Planar depth (metres along the optical axis == world +x) of the forest scene."""
     fx = fy = 0.5 * W
     u = (np.arange(W) + 0.0 - W / 2.0) / fx
@@ -49,7 +49,7 @@ def _depth_image(W, H, cx, cy, cr, origin):
     xn, yn = np.meshgrid(u, v)  # (H, W): cam x right, cam y down
     ox, oy, oz = origin
     # world ray: p(t) = o + t * (1, -xn, -yn)   (T_b_c: body x = cam z, body y = -cam x, body z = -cam y)
-    t = np.full((H, W), 40.0 - ox)  # back wall x = 40
+    t = np.full((H, W), (back_wall - ox) if back_wall is not None else np.inf)  # back wall x = 40, or sky
     with np.errstate(divide="ignore", invalid="ignore"):
         tg = np.where(yn > 1e-9, oz / yn, np.inf)  # ground z = 0
     t = np.minimum(t, tg)
@@ -63,6 +63,8 @@ def _depth_image(W, H, cx, cy, cr, origin):
             tc = (-b - np.sqrt(disc)) / (2 * a)
         tc = np.where((disc > 0) & (tc > 0), tc, np.inf)
         t = np.minimum(t, tc)
+    if back_wall is None:
+        return np.maximum(t, 0.1), xn, yn
     return np.clip(t, 0.1, 100.0), xn, yn
 
 
@@ -88,6 +90,22 @@ def forest_cloud(scene_id: int, npts: int = 50000, body_pos=(0.0, 0.0, D.HEIGHT)
     cloud = pts.reshape(-1, 4)
     edge = np.ascontiguousarray(pts[jump])
     return np.ascontiguousarray(cloud), edge
+
+
+def forest_depth(scene_id: int, rows: int = 480, cols: int = 640, noise: float = 0.02, sky: bool = True,
+                 u16_scale: float = 0.0, body_pos=(0.0, 0.0, D.HEIGHT)) -> np.ndarray:
+    """Full-resolution depth image of the forest scene as the simulator publishes it: 32FC1
+    metres with additive N(0, noise) (airsim_ros_wrapper.cpp:1267-1280),
+    or CV_16UC1 in units of `u16_scale` metres when u16_scale > 0 (0 = no return).  With `sky`
+    the rays that hit nothing carry 1e4 m (beyond depth_max) instead of a back wall."""
+    rng, cx, cy, cr = scene_params(scene_id)
+    origin = (body_pos[0] + D.T_B_C[0, 3], body_pos[1] + D.T_B_C[1, 3], body_pos[2] + D.T_B_C[2, 3])
+    depth, _, _ = _depth_image(cols, rows, cx, cy, cr, origin, back_wall=None if sky else 40.0)
+    hit = np.isfinite(depth)
+    depth = np.where(hit, depth + noise * rng.standard_normal((rows, cols)), 1e4)
+    if u16_scale > 0:
+        return np.where(hit, np.clip(np.rint(depth / u16_scale), 0, 65535), 0).astype(np.uint16)
+    return depth.astype(np.float32)
 
 
 def random_cloud(seed: int, npts: int, lo=(-5, -5, 0), hi=(25, 5, 4)):
