@@ -28,6 +28,7 @@ SYMBOLS = [
     "ampc_round_batch", "ampc_round_batch_dev", "ampc_tick_batch", "ampc_tick_batch_dev", "ampc_last_prefix_dev",
     "ampc_best_of", "ampc_best_of_dev", "ampc_launch_count", "ampc_stream", "ampc_synchronize",
     "ampc_profile_enable", "ampc_profile_get",
+    "ampc_cloud_get", "ampc_set_camera", "ampc_depth_set_batch", "ampc_depth_set_batch_dev",
 ]
 
 
@@ -35,6 +36,16 @@ class Config(C.Structure):
     _fields_ = [("N", C.c_int32), ("K", C.c_int32), ("dt", C.c_double), ("max_batch", C.c_int32),
                 ("max_scenes", C.c_int32), ("max_points", C.c_int32), ("max_edge_points", C.c_int32),
                 ("device", C.c_int32)]
+
+
+class Camera(C.Structure):
+    """perception block of config/mpc_parameters.yaml:58-66 (full-resolution intrinsics)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("resize_scale", C.c_double), ("pixel2meter", C.c_double), ("depth_min", C.c_double),
+                ("depth_max", C.c_double)]
+
+
+DEPTH_F32, DEPTH_U16 = 0, 1
 
 
 class SolverOpts(C.Structure):
@@ -97,6 +108,12 @@ def lib():
         L.ampc_cloud_set_batch.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int64, C.c_int32]
         L.ampc_cloud_set_batch_dev.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_int64, _vp]
         L.ampc_cloud_count.argtypes = [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+        L.ampc_cloud_get.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.POINTER(C.c_int32)]
+        L.ampc_set_camera.argtypes = [_vp, C.POINTER(Camera)]
+        L.ampc_depth_set_batch.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32,
+                                           C.c_int64, C.c_int64, _vp, _vp]
+        L.ampc_depth_set_batch_dev.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32,
+                                               C.c_int64, C.c_int64, _vp, _vp, _vp]
         L.ampc_knn_batch.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
         L.ampc_knn_batch_dev.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp]
         L.ampc_solve_batch.argtypes = [_vp, C.c_int32, _vp, _vp, _vp]
@@ -242,6 +259,43 @@ class Handle:
         n = C.c_int32()
         self._ck(self.L.ampc_cloud_count(self.h, scene, kind, C.byref(n)))
         return n.value
+
+    def cloud_get(self, scene, kind=CLOUD_OBSTACLE):
+        """The cloud held for (scene, kind) as (n, 4) float32 records, in index order."""
+        n = self.cloud_count(scene, kind)
+        out = np.empty((n, 4), dtype=np.float32)
+        m = C.c_int32()
+        self._ck(self.L.ampc_cloud_get(self.h, scene, kind, _ptr(out) if n else None, n, C.byref(m)))
+        return out
+
+    # depth image -> Obstacle + Edge cloud (FrameKDMap::ProcessDepth)
+    def set_camera(self, fx=320.0, fy=320.0, cx=320.0, cy=240.0, resize_scale=10.0, pixel2meter=1.0,
+                   depth_min=0.1, depth_max=100.0):
+        cam = Camera(fx, fy, cx, cy, resize_scale, pixel2meter, depth_min, depth_max)
+        self._ck(self.L.ampc_set_camera(self.h, C.byref(cam)))
+
+    def depth_set_batch(self, depth, T_obstacle, T_edge=None, first_scene=0):
+        """depth: (S, rows, cols) or (rows, cols), float32 or uint16 (host)."""
+        d = np.ascontiguousarray(depth)
+        if d.ndim == 2:
+            d = d[None]
+        if d.dtype not in (np.float32, np.uint16):
+            raise TypeError("depth images are float32 (CV_32FC1) or uint16 (CV_16UC1)")
+        S, rows, cols = d.shape
+        To = _f64(T_obstacle).reshape(S, 16)
+        Te = None if T_edge is None else _f64(T_edge).reshape(S, 16)
+        self._ck(self.L.ampc_depth_set_batch(self.h, first_scene, S, d.ctypes.data,
+                                             DEPTH_U16 if d.dtype == np.uint16 else DEPTH_F32, rows, cols,
+                                             cols * d.itemsize, rows * cols * d.itemsize, To.ctypes.data, _ptr(Te)))
+
+    def depth_set_batch_dev(self, depth_dev, T_obstacle_dev, T_edge_dev=None, first_scene=0, stream=None):
+        """depth_dev: contiguous (S, rows, cols) torch tensor (float32 or int16/uint16 storage) on the
+        handle's device; transforms (S, 16) float64 on the device."""
+        S, rows, cols = depth_dev.shape
+        esz = depth_dev.element_size()
+        self._ck(self.L.ampc_depth_set_batch_dev(self.h, first_scene, S, _ptr(depth_dev),
+                                                 DEPTH_U16 if esz == 2 else DEPTH_F32, rows, cols, cols * esz,
+                                                 rows * cols * esz, _ptr(T_obstacle_dev), _ptr(T_edge_dev), stream))
 
     # k-NN (host buffers)
     def knn(self, queries, k, scene_of=None, kind=CLOUD_OBSTACLE, want_pts=True):

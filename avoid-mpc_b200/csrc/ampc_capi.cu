@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include "ipm_solve.cuh"
 #include "knn_tiles.cuh"
+#include "depth_cloud.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -63,8 +64,14 @@ struct ampc_handle {
     DevBuf cloud[2], counts[2], boxes[2], nan_flags[2];
     int slot_points[2] = {0, 0};
     int slot_tiles[2] = {0, 0};
-    int row_w[2] = {0, 0}; // organised-cloud row pitch hint per kind (0: unorganised)
+    int row_w[2] = {0, 0}; // organised-cloud row pitch hint per kind for the next cloud_set (0: unorganised)
+    DevBuf layout[2];      // per scene: the row pitch its tiles were built with
     DevBuf raw_stage; // staging for stride != 16 uploads
+    // depth image -> clouds
+    ampc_camera cam{320, 320, 320, 240, 10, 1, 0.1, 100}; // config/mpc_parameters.yaml:58-66
+    DevBuf depth_stage, depth_T, depth_tab, depth_scratch, depth_flag;
+    int tab_rows = 0, tab_cols = 0;
+    double tab_scale = 0;
     // batch workspaces
     DevBuf queries, prefix, w, info, knn_idx, knn_d2, knn_cnt, knn_pts, scene_of, x0, ref, posx, replan;
     DevBuf ws_d, ws_i, ws_counter;
@@ -386,7 +393,7 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     P.counts = h->counts[kind].as<int32_t>();
     P.slot_points = h->slot_points[kind];
     P.slot_tiles = h->slot_tiles[kind];
-    P.row_w = h->row_w[kind];
+    P.layout = h->layout[kind].as<int32_t>();
     P.scene_of = scene_of_dev;
     P.active = active;
     P.queries = q_dev;
@@ -435,12 +442,12 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
     if (parts > 65535) parts = 65535;
     cloud_index_kernel<<<dim3(n_scenes, parts), KI_THREADS, 2 * KI_BAND_BYTES, st>>>(
         h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
-        h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->row_w[kind], first_scene);
+        h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->layout[kind].as<int32_t>(), first_scene);
     h->launches++;
     CK(cudaGetLastError());
     cloud_compact_kernel<<<n_scenes, KI_THREADS, 0, st>>>(
         h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
-        h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->row_w[kind], first_scene);
+        h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->layout[kind].as<int32_t>(), first_scene);
     h->launches++;
     CK(cudaGetLastError());
     return prof_end(h, slot, st);
@@ -585,6 +592,10 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
             return bail(e, "cudaMalloc(nan flags)");
         if ((e = cudaMemset(h->nan_flags[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
             return bail(e, "cudaMemset(nan flags)");
+        if ((e = h->layout[kind].reserve((size_t)cfg->max_scenes * 4)) != cudaSuccess)
+            return bail(e, "cudaMalloc(layout)");
+        if ((e = cudaMemset(h->layout[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
+            return bail(e, "cudaMemset(layout)");
     }
     const size_t B = (size_t)cfg->max_batch, N = (size_t)cfg->N, K = (size_t)(cfg->K > 0 ? cfg->K : 1);
     struct { DevBuf *b; size_t n; } need[] = {
@@ -680,6 +691,15 @@ int ampc_synchronize(ampc_handle *h) {
 }
 
 // ---- clouds -----------------------------------------------------------------
+// the scenes being (re)built take the handle's current layout hint
+static int set_layout(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaStream_t st) {
+    fill_i32_kernel<<<(n_scenes + 255) / 256, 256, 0, st>>>(h->layout[kind].as<int32_t>() + first_scene, n_scenes,
+                                                            h->row_w[kind]);
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
+
 static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_scenes, const void *src,
                             bool src_is_device, const int32_t *counts, int64_t scene_stride,
                             int stride, cudaStream_t st) {
@@ -733,6 +753,8 @@ static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_sce
             CK(cudaGetLastError());
         }
     }
+    rc = set_layout(h, kind, first_scene, n_scenes, st);
+    if (rc) return rc;
     return launch_index(h, kind, first_scene, n_scenes, st);
 }
 
@@ -914,7 +936,183 @@ int ampc_cloud_index_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int3
     if (n_scenes < 1 || first_scene < 0 || first_scene + n_scenes > h->cfg.max_scenes)
         return fail(h, AMPC_ERR_CAPACITY, "scene range exceeds ampc_config.max_scenes");
     CK(cudaSetDevice(h->cfg.device));
+    rc = set_layout(h, kind, first_scene, n_scenes, (cudaStream_t)stream);
+    if (rc) return rc;
     return launch_index(h, kind, first_scene, n_scenes, (cudaStream_t)stream);
+}
+
+// ---- depth image -> Obstacle + Edge cloud (FrameKDMap::ProcessDepth, src/FrameKDMap.cpp:90-130)
+int ampc_set_camera(ampc_handle *h, const ampc_camera *cam) {
+    if (!h || !cam) return AMPC_ERR_INVALID;
+    if (!(cam->fx > 0) || !(cam->fy > 0) || !(cam->resize_scale >= 1) || !(cam->pixel2meter > 0) ||
+        !(cam->depth_max > cam->depth_min))
+        return fail(h, AMPC_ERR_INVALID, "bad ampc_camera (need fx, fy, pixel2meter > 0, resize_scale >= 1, depth_max > depth_min)");
+    h->cam = *cam;
+    h->tab_rows = h->tab_cols = 0;
+    return AMPC_OK;
+}
+
+// cv::resize's INTER_LINEAR sampling tables for (rows, cols) -> (H, W), computed as OpenCV
+// does: fx = (float)((dx + 0.5) * scale - 0.5); sx = floor(fx); fx -= sx
+static int depth_tables(ampc_handle *h, int rows, int cols, int H, int W, cudaStream_t st, DepthGeom *g) {
+    const size_t bytes = (size_t)(3 * W + 4 * H) * 4;
+    if (h->tab_rows != rows || h->tab_cols != cols || h->tab_scale != h->cam.resize_scale) {
+        std::vector<int32_t> tab(3 * W + 4 * H);
+        int32_t *xofs = tab.data(), *y0 = tab.data() + 3 * W, *y1 = y0 + H;
+        float *xw0 = reinterpret_cast<float *>(tab.data() + W), *xw1 = xw0 + W;
+        float *yw0 = reinterpret_cast<float *>(y1 + H), *yw1 = yw0 + H;
+        const double sx = 1.0 / ((double)W / cols), sy = 1.0 / ((double)H / rows);
+        for (int d = 0; d < W; ++d) {
+            float f = (float)((d + 0.5) * sx - 0.5);
+            int s = (int)std::floor(f);
+            f -= (float)s;
+            if (s < 0) s = 0, f = 0.f;
+            xofs[d] = s >= cols - 1 ? cols - 1 : s;
+            xw0[d] = 1.f - f;
+            xw1[d] = s >= cols - 1 ? -1.f : f; // right border: the source sample alone
+        }
+        for (int d = 0; d < H; ++d) {
+            float f = (float)((d + 0.5) * sy - 0.5);
+            const int s = (int)std::floor(f);
+            f -= (float)s;
+            y0[d] = s < 0 ? 0 : (s > rows - 1 ? rows - 1 : s);
+            y1[d] = s + 1 < 0 ? 0 : (s + 1 > rows - 1 ? rows - 1 : s + 1);
+            yw0[d] = 1.f - f;
+            yw1[d] = f;
+        }
+        CK(cudaStreamSynchronize(st)); // the previous tables may still be in use
+        CK(h->depth_tab.reserve(bytes));
+        CK(cudaMemcpy(h->depth_tab.p, tab.data(), bytes, cudaMemcpyHostToDevice));
+        h->tab_rows = rows, h->tab_cols = cols, h->tab_scale = h->cam.resize_scale;
+    }
+    int32_t *base = h->depth_tab.as<int32_t>();
+    g->xofs = base;
+    g->xw0 = reinterpret_cast<float *>(base + W);
+    g->xw1 = g->xw0 + W;
+    g->y0 = base + 3 * W;
+    g->y1 = g->y0 + H;
+    g->yw0 = reinterpret_cast<float *>(base + 3 * W + 2 * H);
+    g->yw1 = g->yw0 + H;
+    return AMPC_OK;
+}
+
+int ampc_depth_set_batch_dev(ampc_handle *h, int32_t first_scene, int32_t n_scenes, const void *depth_dev,
+                             int32_t dtype, int32_t rows, int32_t cols, int64_t row_stride_bytes,
+                             int64_t image_stride_bytes, const double *T_obstacle_dev, const double *T_edge_dev,
+                             void *stream) {
+    if (!h) return AMPC_ERR_INVALID;
+    int rc = check_kind(h, AMPC_CLOUD_OBSTACLE);
+    if (rc) return rc;
+    if (n_scenes < 1 || first_scene < 0 || first_scene + n_scenes > h->cfg.max_scenes)
+        return fail(h, AMPC_ERR_CAPACITY, "scene range exceeds ampc_config.max_scenes");
+    if (!depth_dev || !T_obstacle_dev) return fail(h, AMPC_ERR_INVALID, "null depth image or transform");
+    if (dtype != AMPC_DEPTH_F32 && dtype != AMPC_DEPTH_U16)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "depth dtype must be AMPC_DEPTH_F32 or AMPC_DEPTH_U16"); // :96-103
+    const int esz = dtype == AMPC_DEPTH_U16 ? 2 : 4;
+    if (rows < 1 || cols < 1 || row_stride_bytes < (int64_t)cols * esz || (row_stride_bytes % esz) ||
+        (n_scenes > 1 && image_stride_bytes < row_stride_bytes * rows) || (image_stride_bytes % esz))
+        return fail(h, AMPC_ERR_INVALID, "bad depth image geometry");
+    const int W = (int)(cols / h->cam.resize_scale), H = (int)(rows / h->cam.resize_scale); // :106-107
+    if (W < 1 || H < 1) return fail(h, AMPC_ERR_INVALID, "resize_scale leaves no pixels");
+    if ((int64_t)W * H > h->slot_points[0])
+        return fail(h, AMPC_ERR_CAPACITY, "resized image has more pixels than ampc_config.max_points");
+    const bool with_edge = h->slot_points[1] > 0;
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    DepthGeom g{};
+    g.fx = h->cam.fx / h->cam.resize_scale, g.fy = h->cam.fy / h->cam.resize_scale;
+    g.cx = h->cam.cx / h->cam.resize_scale, g.cy = h->cam.cy / h->cam.resize_scale;
+    g.p2m = h->cam.pixel2meter, g.dmin = h->cam.depth_min, g.dmax = h->cam.depth_max;
+    g.range = h->cam.depth_max - h->cam.depth_min;
+    g.rows = rows, g.cols = cols, g.H = H, g.W = W;
+    g.is_u16 = dtype == AMPC_DEPTH_U16, g.identity = (W == cols && H == rows);
+    g.row_stride = row_stride_bytes, g.image_stride = image_stride_bytes;
+    rc = depth_tables(h, rows, cols, H, W, st, &g);
+    if (rc) return rc;
+    const size_t npx = (size_t)H * W;
+    if (h->depth_scratch.bytes < (size_t)n_scenes * npx * 4) {
+        CK(cudaStreamSynchronize(st));
+        CK(h->depth_scratch.reserve((size_t)n_scenes * npx * 4));
+    }
+    if (!h->depth_flag.p) {
+        CK(h->depth_flag.reserve(4));
+        CK(cudaMemset(h->depth_flag.p, 0, 4));
+    }
+    unsigned char *infl = h->depth_scratch.as<unsigned char>();
+    unsigned char *er = infl + (size_t)n_scenes * npx;
+    unsigned short *mag = reinterpret_cast<unsigned short *>(er + (size_t)n_scenes * npx);
+    int slot;
+    rc = prof_begin(h, SEC_INDEX, st, &slot);
+    if (rc) return rc;
+    depth_obstacle_kernel<<<n_scenes, DC_THREADS, 0, st>>>(
+        g, static_cast<const unsigned char *>(depth_dev), T_obstacle_dev, h->cloud[0].as<float4>(),
+        h->counts[0].as<int32_t>(), h->layout[0].as<int32_t>(), infl, h->depth_flag.as<int32_t>(),
+        h->slot_points[0], first_scene);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (with_edge) {
+        edge_grad_kernel<<<dim3((W + EG_BX - 1) / EG_BX, (H + EG_BY - 1) / EG_BY, n_scenes), dim3(EG_BX, EG_BY), 0, st>>>(
+            H, W, infl, er, mag);
+        h->launches++;
+        CK(cudaGetLastError());
+        edge_cloud_kernel<<<n_scenes, DC_THREADS, 0, st>>>(
+            g, T_edge_dev ? T_edge_dev : T_obstacle_dev, er, mag, h->cloud[1].as<float4>(),
+            h->counts[1].as<int32_t>(), h->layout[1].as<int32_t>(), h->counts[0].as<int32_t>(),
+            h->depth_flag.as<int32_t>(), h->slot_points[1], first_scene);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    rc = prof_end(h, slot, st);
+    if (rc) return rc;
+    rc = launch_index(h, AMPC_CLOUD_OBSTACLE, first_scene, n_scenes, st);
+    if (rc || !with_edge) return rc;
+    return launch_index(h, AMPC_CLOUD_EDGE, first_scene, n_scenes, st);
+}
+
+int ampc_depth_set_batch(ampc_handle *h, int32_t first_scene, int32_t n_scenes, const void *depth_host,
+                         int32_t dtype, int32_t rows, int32_t cols, int64_t row_stride_bytes,
+                         int64_t image_stride_bytes, const double *T_obstacle, const double *T_edge) {
+    if (!h) return AMPC_ERR_INVALID;
+    if (!depth_host || !T_obstacle || n_scenes < 1 || rows < 1 || row_stride_bytes < 1)
+        return fail(h, AMPC_ERR_INVALID, "null depth image or transform");
+    if (n_scenes == 1) image_stride_bytes = row_stride_bytes * rows;
+    if (image_stride_bytes < row_stride_bytes * rows)
+        return fail(h, AMPC_ERR_INVALID, "bad depth image geometry");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const size_t img_bytes = (size_t)image_stride_bytes * n_scenes, t_bytes = (size_t)n_scenes * 16 * 8;
+    CK(cudaStreamSynchronize(st));
+    CK(h->depth_stage.reserve(img_bytes));
+    CK(h->depth_T.reserve(2 * t_bytes));
+    CK(cudaMemcpyAsync(h->depth_stage.p, depth_host, img_bytes, cudaMemcpyHostToDevice, st));
+    double *Td = h->depth_T.as<double>();
+    CK(cudaMemcpyAsync(Td, T_obstacle, t_bytes, cudaMemcpyHostToDevice, st));
+    if (T_edge) CK(cudaMemcpyAsync(Td + (size_t)n_scenes * 16, T_edge, t_bytes, cudaMemcpyHostToDevice, st));
+    int rc = ampc_depth_set_batch_dev(h, first_scene, n_scenes, h->depth_stage.p, dtype, rows, cols,
+                                      row_stride_bytes, image_stride_bytes, Td,
+                                      T_edge ? Td + (size_t)n_scenes * 16 : nullptr, st);
+    if (rc) return rc;
+    int32_t flag = 0;
+    CK(cudaMemcpyAsync(&flag, h->depth_flag.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flag) {
+        CK(cudaMemset(h->depth_flag.p, 0, 4));
+        return fail(h, AMPC_ERR_CAPACITY, "a cloud built from a depth image exceeded its slot capacity and was truncated");
+    }
+    return AMPC_OK;
+}
+
+int ampc_cloud_get(ampc_handle *h, int32_t scene, int32_t kind, void *xyz16_out, int32_t max_points,
+                   int32_t *n_out) {
+    if (!h || !n_out) return AMPC_ERR_INVALID;
+    int rc = ampc_cloud_count(h, scene, kind, n_out);
+    if (rc) return rc;
+    if (*n_out > max_points || (!xyz16_out && *n_out > 0))
+        return fail(h, AMPC_ERR_CAPACITY, "output buffer smaller than the cloud");
+    if (*n_out > 0)
+        CK(cudaMemcpy(xyz16_out, h->cloud[kind].as<float4>() + (int64_t)scene * h->slot_points[kind],
+                      (size_t)*n_out * 16, cudaMemcpyDeviceToHost));
+    return AMPC_OK;
 }
 
 int ampc_profile_enable(ampc_handle *h, int on) {

@@ -94,7 +94,7 @@ struct KnnParams {
     const int32_t *counts;   // points held in each slot (after the NaN filter)
     int64_t slot_points;
     int64_t slot_tiles;
-    int32_t row_w;           // 0: unorganised cloud; >0: row pitch for 8x8 patch tiles
+    const int32_t *layout;   // per scene: 0 = unorganised cloud; >0 = row pitch for 8x8 patch tiles
     const int32_t *scene_of; // [B] or nullptr (identity)
     const int32_t *active;   // [B] or nullptr: instances with 0 are skipped (outputs untouched)
     const double *queries;   // [B][Q][3]
@@ -206,11 +206,12 @@ constexpr int KI_BAND_BYTES = 8 * KI_COLS * 16; // 32 KB per buffer
 __global__ void __launch_bounds__(KI_THREADS)
 cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes,
                    const int32_t *__restrict__ counts, int32_t *__restrict__ nan_flags,
-                   int64_t slot_points, int64_t slot_tiles, int row_w, int first_scene) {
+                   int64_t slot_points, int64_t slot_tiles, const int32_t *__restrict__ layout, int first_scene) {
     extern __shared__ __align__(128) unsigned char ki_smem[];
     __shared__ __align__(8) unsigned long long bar[2];
     float4 *buf[2] = {reinterpret_cast<float4 *>(ki_smem), reinterpret_cast<float4 *>(ki_smem + KI_BAND_BYTES)};
     const int scene = first_scene + blockIdx.x; // scenes on x: no 65535 limit
+    const int row_w = layout[scene];
     const float4 *c = clouds + (int64_t)scene * slot_points;
     float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
     const int n = counts[scene];
@@ -312,10 +313,11 @@ cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes
 // then the boxes are rebuilt over the compacted cloud.
 __global__ void __launch_bounds__(KI_THREADS)
 cloud_compact_kernel(float4 *clouds, float4 *boxes, int32_t *counts, int32_t *nan_flags,
-                     int64_t slot_points, int64_t slot_tiles, int row_w, int first_scene) {
+                     int64_t slot_points, int64_t slot_tiles, const int32_t *layout, int first_scene) {
     const int scene = first_scene + blockIdx.x;
     if (nan_flags[scene] == 0)
         return;
+    const int row_w = layout[scene];
     float4 *c = clouds + (int64_t)scene * slot_points;
     float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
     const int n = counts[scene];
@@ -568,7 +570,7 @@ knn_search_kernel(const KnnParams P) {
     const float4 *boxes = P.boxes + (int64_t)scene * P.slot_tiles * 2;
     const double *qp = P.queries + ((int64_t)b * P.Q + q) * 3;
     const double qx = qp[0], qy = qp[1], qz = qp[2];
-    const TileGeom g(n, P.row_w);
+    const TileGeom g(n, P.layout[scene]);
     const int n_tiles = g.n_tiles;
     const int per = (n_tiles + P.segs - 1) / P.segs;
     const int t_begin = seg * per, t_end = min(n_tiles, t_begin + per);

@@ -38,8 +38,8 @@ Mat4 Mat4Identity() { return {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}; }
 FrameKDMap::FrameKDMap(int maxPoints, int maxEdgePoints, const MapParams &p) : mP(p) {
     ampc_config cfg{};
     cfg.N = 1, cfg.K = 1, cfg.dt = 1.0;
-    cfg.max_batch = std::max(64, p.maxFrameCount + 2);
-    cfg.max_scenes = p.maxFrameCount + 2; // slot 0 = current frame, the rest = key-frames
+    cfg.max_batch = std::max(64, p.maxFrameCount + 4);
+    cfg.max_scenes = p.maxFrameCount + 4; // current frame, the frame being built, key-frames (+1 before pruning)
     cfg.max_points = maxPoints;
     cfg.max_edge_points = maxEdgePoints;
     cfg.device = 0;
@@ -47,40 +47,89 @@ FrameKDMap::FrameKDMap(int maxPoints, int maxEdgePoints, const MapParams &p) : m
     if (ampc_create(&cfg, &h) != AMPC_OK)
         die(nullptr, "ampc_create");
     mHandle.reset(h, ampc_destroy);
-    for (int s = cfg.max_scenes - 1; s >= 1; --s)
-        mFreeSlots.push_back(s);
-    mCur.slot = 0;
-    mCur.Twc = Mat4Identity();
+    ampc_camera cam{p.fx, p.fy, p.cx, p.cy, p.resizeScale, p.pixel2Meter, p.depthMin, p.depthMax};
+    if (ampc_set_camera(h, &cam) != AMPC_OK)
+        die(h, "ampc_set_camera");
+    mFreeSlots = std::make_shared<std::vector<int>>();
+    for (int s = cfg.max_scenes - 1; s >= 0; --s)
+        mFreeSlots->push_back(s);
+    mCur.Twc = Mat4Identity(); // the reference leaves Frame::Twc uninitialised until the first AddVertex
 }
 
-void FrameKDMap::Upload(Frame &f) {
-    const std::vector<pcl::PointXYZ> *src[2] = {&f.pts, &f.edge};
+std::shared_ptr<FrameKDMap::Cloud> FrameKDMap::NewCloud() {
+    if (mFreeSlots->empty())
+        throw std::runtime_error("FrameKDMap(GPU): out of scene slots");
+    Cloud *c = new Cloud();
+    c->slot = mFreeSlots->back();
+    mFreeSlots->pop_back();
+    std::shared_ptr<std::vector<int>> pool = mFreeSlots;
+    return std::shared_ptr<Cloud>(c, [pool](Cloud *p) {
+        pool->push_back(p->slot);
+        delete p;
+    });
+}
+
+void FrameKDMap::RefreshCounts(Cloud &c) {
     for (int kind = 0; kind < 2; ++kind) {
-        if (ampc_cloud_set(mHandle.get(), f.slot, kind, src[kind]->data(), (int)src[kind]->size(), 16) != AMPC_OK)
-            die(mHandle.get(), "ampc_cloud_set");
         int32_t n = 0;
-        if (ampc_cloud_count(mHandle.get(), f.slot, kind, &n) != AMPC_OK)
+        if (ampc_cloud_count(mHandle.get(), c.slot, kind, &n) != AMPC_OK)
             die(mHandle.get(), "ampc_cloud_count");
-        f.count[kind] = n; // after the NaN filter of KDTreeTwo::Initialize (kd_tree_two.h:99-101)
+        c.count[kind] = n; // after the NaN filter of KDTreeTwo::Initialize (kd_tree_two.h:99-101)
     }
+}
+
+std::vector<pcl::PointXYZ> FrameKDMap::Download(const Cloud &c, int kind) {
+    static_assert(sizeof(pcl::PointXYZ) == 16, "pcl::PointXYZ is a 16-byte record");
+    std::vector<pcl::PointXYZ> pts(c.count[kind]);
+    int32_t n = 0;
+    if (ampc_cloud_get(mHandle.get(), c.slot, kind, pts.data(), (int32_t)pts.size(), &n) != AMPC_OK)
+        die(mHandle.get(), "ampc_cloud_get");
+    pts.resize(n);
+    return pts;
+}
+
+std::vector<pcl::PointXYZ> FrameKDMap::CurrentPoints(bool edge) {
+    return mCur.cloud ? Download(*mCur.cloud, edge ? 1 : 0) : std::vector<pcl::PointXYZ>();
+}
+
+void FrameKDMap::AddVertex(const Mat4 &Twb, const DepthImage &depth) {
+    if (!depth.data || depth.rows < 1 || depth.cols < 1)
+        throw std::runtime_error("FrameKDMap(GPU): empty depth image");
+    const Mat4 Twc = mul(Twb, mP.Tbc);        // :117-119
+    const Mat4 Tedge = mul(mCur.Twc, mP.Tbc); // mCurFrame.Twc (previous frame) * mParamTbc, :208-209
+    std::shared_ptr<Cloud> c = NewCloud();
+    const size_t step = depth.step ? depth.step : (size_t)depth.cols * (depth.isU16 ? 2 : 4);
+    if (ampc_depth_set_batch(mHandle.get(), c->slot, 1, depth.data, depth.isU16 ? AMPC_DEPTH_U16 : AMPC_DEPTH_F32,
+                             depth.rows, depth.cols, (int64_t)step, 0, Twc.data(), Tedge.data()) != AMPC_OK)
+        die(mHandle.get(), "ampc_depth_set_batch");
+    mP.width = (int)(depth.cols / mP.resizeScale); // :106-107
+    mP.height = (int)(depth.rows / mP.resizeScale);
+    RefreshCounts(*c);
+    if (c->count[0] == 0)
+        return; // :41-43: the previous frame stays current
+    mCur.cloud = c;
+    mCur.Twc = Twc;
+    mHaveCur = true;
+}
+
+void FrameKDMap::Upload(Cloud &c, int kind, const std::vector<pcl::PointXYZ> &pts) {
+    if (ampc_cloud_set(mHandle.get(), c.slot, kind, pts.data(), (int)pts.size(), 16) != AMPC_OK)
+        die(mHandle.get(), "ampc_cloud_set");
 }
 
 void FrameKDMap::AddClouds(const CloudPtr &cloud, const CloudPtr &edgeCloud, const Mat4 &Twc, int rowWidthHint) {
     if (ampc_cloud_set_layout(mHandle.get(), AMPC_CLOUD_OBSTACLE, rowWidthHint) != AMPC_OK)
         die(mHandle.get(), "ampc_cloud_set_layout");
-    mCur.pts.clear();
-    for (const auto &p : cloud->points) // keep the host copy NaN-filtered like the tree's own copy
-        if (!(p.x != p.x))
-            mCur.pts.push_back(p);
-    mCur.edge.clear();
-    for (const auto &p : edgeCloud->points)
-        if (!(p.x != p.x))
-            mCur.edge.push_back(p);
+    std::shared_ptr<Cloud> c = NewCloud();
+    Upload(*c, 0, cloud->points);
+    Upload(*c, 1, edgeCloud->points);
+    if (ampc_cloud_set_layout(mHandle.get(), AMPC_CLOUD_OBSTACLE, 0) != AMPC_OK)
+        die(mHandle.get(), "ampc_cloud_set_layout");
+    RefreshCounts(*c);
+    mCur.cloud = c;
     mCur.Twc = Twc;
-    Upload(mCur);
     mHaveCur = true;
 }
-
 bool FrameKDMap::PtIsInFrame(const Eigen::Vector3d &ptw, const Mat4 &Twc) const { // :215-231
     const Mat4 Tcw = rigid_inverse(Twc);
     const double x = Tcw[0] * ptw.x() + Tcw[1] * ptw.y() + Tcw[2] * ptw.z() + Tcw[3];
@@ -88,7 +137,8 @@ bool FrameKDMap::PtIsInFrame(const Eigen::Vector3d &ptw, const Mat4 &Twc) const 
     const double z = Tcw[8] * ptw.x() + Tcw[9] * ptw.y() + Tcw[10] * ptw.z() + Tcw[11];
     if (z > mP.depthMax || z < 0)
         return false;
-    const double u = mP.fx * x / z + mP.cx, v = mP.fy * y / z + mP.cy;
+    const double sc = mP.resizeScale; // intrinsics of the resized image, :21-24
+    const double u = (mP.fx / sc) * x / z + mP.cx / sc, v = (mP.fy / sc) * y / z + mP.cy / sc;
     return !(u < 0 || u >= mP.width || v < 0 || v >= mP.height);
 }
 
@@ -115,14 +165,14 @@ void FrameKDMap::SearchFrames(const std::vector<const Frame *> &frames, const Ei
     std::vector<int32_t> scene_of(F), cnt(F);
     std::vector<double> q(3 * F), dd((size_t)F * k), pp((size_t)F * k * 3);
     for (int f = 0; f < F; ++f) {
-        scene_of[f] = frames[f]->slot;
+        scene_of[f] = frames[f]->cloud->slot;
         q[3 * f] = p.x(), q[3 * f + 1] = p.y(), q[3 * f + 2] = p.z();
     }
     if (ampc_knn_batch(mHandle.get(), kind, F, scene_of.data(), q.data(), 1, k, nullptr, dd.data(), pp.data(),
                        cnt.data()) != AMPC_OK)
         die(mHandle.get(), "ampc_knn_batch");
     for (int f = 0; f < F; ++f) {
-        if (frames[f]->count[kind] <= k)
+        if (frames[f]->cloud->count[kind] <= k)
             continue; // n < k asks for n and gets none; n == k gets none
         for (int j = 0; j < cnt[f]; ++j) {
             const double *c = &pp[((size_t)f * k + j) * 3];
@@ -139,7 +189,7 @@ void FrameKDMap::QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, i
     out.assign(Q, {});
     distances.assign(Q, {});
     const int kind = queryEdge ? AMPC_CLOUD_EDGE : AMPC_CLOUD_OBSTACLE;
-    const int n = mCur.count[kind];
+    const int n = mCur.cloud ? mCur.cloud->count[kind] : 0;
     if (Q == 0 || n == 0 || k <= 0)
         return;
     const int kq = k < n ? k : n;
@@ -147,7 +197,7 @@ void FrameKDMap::QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, i
     std::vector<int32_t> cnt(Q);
     for (int i = 0; i < Q; ++i)
         q[3 * i] = points[i].x(), q[3 * i + 1] = points[i].y(), q[3 * i + 2] = points[i].z();
-    const int32_t scene0 = mCur.slot;
+    const int32_t scene0 = mCur.cloud->slot;
     if (ampc_knn_batch(mHandle.get(), kind, 1, &scene0, q.data(), Q, kq, nullptr, d2.data(), pts.data(),
                        cnt.data()) != AMPC_OK)
         die(mHandle.get(), "ampc_knn_batch");
@@ -165,7 +215,7 @@ void FrameKDMap::QueryNearest(const Eigen::Vector3d &point, int k, std::vector<E
     distances.clear();
     const int kind = queryEdge ? AMPC_CLOUD_EDGE : AMPC_CLOUD_OBSTACLE;
     // fast path (:329-346): the current frame alone
-    if (mHaveCur && mCur.count[kind] >= k && PtIsInFrame(point, mCur.Twc)) {
+    if (mHaveCur && mCur.cloud->count[kind] >= k && PtIsInFrame(point, mCur.Twc)) {
         std::vector<std::vector<Eigen::Vector3d>> o;
         std::vector<std::vector<double>> d;
         QueryNearestBatch({point}, k, o, d, queryEdge);
@@ -195,7 +245,7 @@ double FrameKDMap::GetNearestDistance(const Eigen::Vector3d &point) { // :400-42
         return nearest; // returned un-rooted (:402-404)
     std::vector<const Frame *> frames;
     for (const Frame *f : all)
-        if (f->count[0] > 0) // frames with an empty Obstacle cloud are skipped (:383-386)
+        if (f->cloud->count[0] > 0) // frames with an empty Obstacle cloud are skipped (:383-386)
             frames.push_back(f);
     std::vector<std::vector<Eigen::Vector3d>> pts;
     std::vector<std::vector<double>> d2;
@@ -209,14 +259,14 @@ double FrameKDMap::GetNearestDistance(const Eigen::Vector3d &point) { // :400-42
 bool FrameKDMap::DroneBehindPts(const Mat4 &Twc, const Frame &frame) { // :233-252
     const Mat4 Twb = mul(Twc, rigid_inverse(mP.Tbc));
     const Eigen::Vector3d twb(Twb[3], Twb[7], Twb[11]);
-    const int ptsCount = std::min(frame.count[0], 10);
+    const int ptsCount = std::min(frame.cloud->count[0], 10);
     std::vector<std::vector<Eigen::Vector3d>> pts;
     std::vector<std::vector<double>> d2;
     if (ptsCount > 0) {
         // SearchForNearest(twb, ptsCount) on that frame: nothing when the frame holds exactly ptsCount points
         std::vector<int32_t> cnt(1);
         std::vector<double> q = {twb.x(), twb.y(), twb.z()}, dd(ptsCount), pp(3 * (size_t)ptsCount);
-        const int32_t slot = frame.slot;
+        const int32_t slot = frame.cloud->slot;
         if (ampc_knn_batch(mHandle.get(), AMPC_CLOUD_OBSTACLE, 1, &slot, q.data(), 1, ptsCount, nullptr, dd.data(),
                            pp.data(), cnt.data()) != AMPC_OK)
             die(mHandle.get(), "ampc_knn_batch");
@@ -231,23 +281,15 @@ bool FrameKDMap::DroneBehindPts(const Mat4 &Twc, const Frame &frame) { // :233-2
     return true;
 }
 
-void FrameKDMap::InsertKeyFrame() { // :428-432: the key-frame is the current frame's snapshot
+void FrameKDMap::InsertKeyFrame() { // :428-432: the key-frame shares the current frame's trees
     if (!mHaveCur)
         return;
-    if (mFreeSlots.empty())
-        RemoveOldVertex();
-    Frame f = mCur;
-    f.slot = mFreeSlots.back();
-    mFreeSlots.pop_back();
-    Upload(f);
-    mKeyFrames.push_back(std::move(f));
+    mKeyFrames.push_back(mCur);
 }
 
 void FrameKDMap::RemoveOldVertex() { // :59-63
-    if (mKeyFrames.empty())
-        return;
-    mFreeSlots.push_back(mKeyFrames.front().slot);
-    mKeyFrames.pop_front();
+    if (!mKeyFrames.empty())
+        mKeyFrames.pop_front();
 }
 
 void FrameKDMap::ProcessKeyframes() { // body of KeyframeThreadWorker, :446-487
@@ -266,25 +308,26 @@ void FrameKDMap::ProcessKeyframes() { // body of KeyframeThreadWorker, :446-487
     if (mKeyFrames.empty())
         return;
     // points of the last key-frame farther than keyframe_th_dist from the current cloud
-    Frame &last = mKeyFrames.back();
-    const int n = (int)last.pts.size();
+    Cloud &last = *mKeyFrames.back().cloud;
+    const std::vector<pcl::PointXYZ> lastPts = Download(last, 0);
+    const int n = (int)lastPts.size();
     std::vector<pcl::PointXYZ> outliers;
-    if (n > 0 && mCur.count[0] > 0) {
+    if (n > 0 && mCur.cloud->count[0] > 0) {
         std::vector<double> q(3 * (size_t)n), d2(n);
         std::vector<int32_t> cnt(n);
         for (int i = 0; i < n; ++i)
-            q[3 * i] = last.pts[i].x, q[3 * i + 1] = last.pts[i].y, q[3 * i + 2] = last.pts[i].z;
-        const int32_t slot = mCur.slot;
+            q[3 * i] = lastPts[i].x, q[3 * i + 1] = lastPts[i].y, q[3 * i + 2] = lastPts[i].z;
+        const int32_t slot = mCur.cloud->slot;
         if (ampc_knn_batch(mHandle.get(), AMPC_CLOUD_OBSTACLE, 1, &slot, q.data(), n, 1, nullptr, d2.data(), nullptr,
                            cnt.data()) != AMPC_OK)
             die(mHandle.get(), "ampc_knn_batch");
         for (int i = 0; i < n; ++i)
             if (cnt[i] > 0 && std::sqrt(d2[i]) > mP.keyframeDistanceTh)
-                outliers.push_back(last.pts[i]);
+                outliers.push_back(lastPts[i]);
     }
     if ((int)outliers.size() < mP.keyframeCountTh)
         return;
-    last.pts = outliers; // lastPtCloudPtr->InitializeNew(newCloud), :484
-    Upload(last);
+    Upload(last, 0, outliers); // lastPtCloudPtr->InitializeNew(newCloud), :484: in place, seen by every frame sharing it
+    RefreshCounts(last);
     InsertKeyFrame();
 }

@@ -8,8 +8,9 @@
 //                       only the outlier points of the last one, insert the current frame
 // Every frame (current + key-frames) is one scene slot of the handle; a multi-frame query is ONE
 // batched k-NN launch over the frames instead of the reference's per-query std::thread fan-out.
-// Not ported: building the two clouds from the depth image
-// (ProcessDepth/BuildEdgeCloud, :90-214) -- the clouds are handed in ready-made (AddClouds).
+//   AddVertex           depth image -> Obstacle + Edge cloud + their indices, all on the device
+//                       (ProcessDepth / BuildEdgeCloud incl. the OpenCV calls, :36-53,76-214)
+// AddClouds is the same entry for callers that already hold the two clouds.
 #ifndef FRAME_KD_MAP_H
 #define FRAME_KD_MAP_H
 #include "../../include/ampc.h"
@@ -24,9 +25,17 @@
 using Mat4 = std::array<double, 16>; // row-major homogeneous transform
 Mat4 Mat4Identity();
 
-struct MapParams { // config/mpc_parameters.yaml:59-75, already divided by resize_scale (:FrameKDMap.cpp:21-24)
-    double fx = 32, fy = 32, cx = 32, cy = 24;
-    int width = 64, height = 48;      // mParamWidth / mParamHeight (set in ProcessDepth, :106-107)
+struct DepthImage { // what cv_bridge hands ProcessDepth (:94): CV_32FC1 metres or CV_16UC1
+    const void *data = nullptr;
+    int rows = 0, cols = 0;
+    bool isU16 = false;
+    size_t step = 0; // bytes per row; 0 = tightly packed
+};
+
+struct MapParams { // config/mpc_parameters.yaml:58-75; fx..cy at full resolution, as in the yaml
+    double fx = 320, fy = 320, cx = 320, cy = 240;
+    double resizeScale = 10, pixel2Meter = 1;
+    int width = 64, height = 48;      // mParamWidth / mParamHeight: set by AddVertex (:106-107), or by the caller
     double depthMax = 100, depthMin = 0.1;
     double keyframeDistanceTh = 0.1;  // keyframe_th_dist
     int keyframeCountTh = 10;         // keyframe_th_count
@@ -38,7 +47,9 @@ class FrameKDMap {
 public:
     explicit FrameKDMap(int maxPoints = 65536, int maxEdgePoints = 16384, const MapParams &p = MapParams());
     using CloudPtr = pcl::PointCloud<pcl::PointXYZ>::Ptr;
-    // replaces AddVertex's two InitializeNew calls + swap into mCurFrame (:44-51); Twc = Twb * Tbc
+    // AddVertex (:36-53): a frame whose Obstacle cloud comes out empty is dropped (:41-43)
+    void AddVertex(const Mat4 &Twb, const DepthImage &depth);
+    // the two InitializeNew calls + swap into mCurFrame (:44-51) for ready-made clouds; Twc = Twb * Tbc
     void AddClouds(const CloudPtr &cloud, const CloudPtr &edgeCloud, const Mat4 &Twc = Mat4Identity(),
                    int rowWidthHint = 0);
     void QueryNearest(const Eigen::Vector3d &point, int nearestPointCount,
@@ -54,29 +65,37 @@ public:
     void InsertKeyFrame();
     void RemoveOldVertex();
     int KeyFrameCount() const { return (int)mKeyFrames.size(); }
-    int KeyFramePointCount(int i, bool edge = false) const { return mKeyFrames[i].count[edge ? 1 : 0]; }
-    int PointCount(bool edge) const { return mCur.count[edge ? 1 : 0]; }
+    int KeyFramePointCount(int i, bool edge = false) const { return mKeyFrames[i].cloud->count[edge ? 1 : 0]; }
+    int PointCount(bool edge) const { return mCur.cloud ? mCur.cloud->count[edge ? 1 : 0] : 0; }
+    // host copy of the current frame's cloud (KDTreeTwo::GetPointCloud().pts)
+    std::vector<pcl::PointXYZ> CurrentPoints(bool edge = false);
     bool PtIsInFrame(const Eigen::Vector3d &ptw, const Mat4 &Twc) const;
     ampc_handle *Handle() { return mHandle.get(); }
 
 private:
-    struct Frame {
+    // one scene slot of the handle = the pair of trees a reference Frame points to; shared between
+    // the current frame and the key-frame made from it, like the reference's shared_ptr<KDTreeTwo>
+    struct Cloud {
         int slot = 0;
         int count[2] = {0, 0};
-        Mat4 Twc;
-        std::vector<pcl::PointXYZ> pts; // host copy of the Obstacle cloud (outlier step, snapshots)
-        std::vector<pcl::PointXYZ> edge;
     };
-    void Upload(Frame &f);
+    struct Frame {
+        std::shared_ptr<Cloud> cloud;
+        Mat4 Twc;
+    };
+    std::shared_ptr<Cloud> NewCloud();
+    void Upload(Cloud &c, int kind, const std::vector<pcl::PointXYZ> &pts);
+    std::vector<pcl::PointXYZ> Download(const Cloud &c, int kind);
+    void RefreshCounts(Cloud &c);
     bool DroneBehindPts(const Mat4 &Twc, const Frame &frame);
     std::vector<const Frame *> QueryVector() const; // UpdateQueryVector (:65-75)
     void SearchFrames(const std::vector<const Frame *> &frames, const Eigen::Vector3d &p, int k, int kind,
                       std::vector<std::vector<Eigen::Vector3d>> &pts, std::vector<std::vector<double>> &d2);
     std::shared_ptr<ampc_handle> mHandle;
     MapParams mP;
+    std::shared_ptr<std::vector<int>> mFreeSlots; // outlives every Cloud
     Frame mCur;
     std::deque<Frame> mKeyFrames;
-    std::vector<int> mFreeSlots;
     bool mHaveCur = false;
 };
 #endif

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <random>
 
 #define CHECK(c)                                                                                   \
@@ -15,7 +16,56 @@
         }                                                                                          \
     } while (0)
 
-int main() {
+// AddVertex on two depth frames written by tests/test_gpu_shim.py together with the clouds the
+// test expects for the second one (Edge points use the FIRST frame's Twc, FrameKDMap.cpp:208-209)
+static int depth_case(const char *path) {
+    FILE *f = std::fopen(path, "rb");
+    CHECK(f != nullptr);
+    int32_t hd[4];
+    double par[8], Twb0[16], Twb1[16];
+    CHECK(std::fread(hd, 4, 4, f) == 4 && std::fread(par, 8, 8, f) == 8);
+    CHECK(std::fread(Twb0, 8, 16, f) == 16 && std::fread(Twb1, 8, 16, f) == 16);
+    const int rows = hd[0], cols = hd[1], nc = hd[2], ne = hd[3];
+    std::vector<float> d0((size_t)rows * cols), d1(d0.size()), cloud((size_t)nc * 4), edge((size_t)ne * 4);
+    CHECK(std::fread(d0.data(), 4, d0.size(), f) == d0.size() && std::fread(d1.data(), 4, d1.size(), f) == d1.size());
+    CHECK(std::fread(cloud.data(), 4, cloud.size(), f) == cloud.size());
+    CHECK(std::fread(edge.data(), 4, edge.size(), f) == edge.size());
+    std::fclose(f);
+    MapParams mp;
+    mp.fx = par[0], mp.fy = par[1], mp.cx = par[2], mp.cy = par[3], mp.resizeScale = par[4], mp.pixel2Meter = par[5];
+    mp.depthMin = par[6], mp.depthMax = par[7], mp.maxFrameCount = 2;
+    const int H = (int)(rows / mp.resizeScale), W = (int)(cols / mp.resizeScale);
+    FrameKDMap map(H * W, H * W, mp);
+    Mat4 T0, T1;
+    std::copy(Twb0, Twb0 + 16, T0.begin());
+    std::copy(Twb1, Twb1 + 16, T1.begin());
+    DepthImage img;
+    img.rows = rows, img.cols = cols;
+    img.data = d0.data();
+    map.AddVertex(T0, img);
+    CHECK(map.PointCount(false) > 0);
+    std::vector<float> sky(d0.size(), 1e4f); // nothing in range: the frame is dropped, frame 0 stays
+    img.data = sky.data();
+    const int before = map.PointCount(false);
+    map.AddVertex(T1, img);
+    CHECK(map.PointCount(false) == before);
+    img.data = d1.data();
+    map.AddVertex(T1, img);
+    CHECK(map.PointCount(false) == nc && map.PointCount(true) == ne);
+    const auto pc = map.CurrentPoints(false), pe = map.CurrentPoints(true);
+    CHECK(std::memcmp(pc.data(), cloud.data(), cloud.size() * 4) == 0);
+    CHECK(std::memcmp(pe.data(), edge.data(), edge.size() * 4) == 0);
+    std::vector<Eigen::Vector3d> out;
+    std::vector<double> dist;
+    map.QueryNearest(Eigen::Vector3d(cloud[0], cloud[1], cloud[2]), 4, out, dist);
+    CHECK(dist.size() == 4 && dist[0] == 0.0);
+    std::printf("depth frames ok: %d obstacle points, %d edge points\n", nc, ne);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && depth_case(argv[1]) != 0)
+        return 1;
     std::mt19937 rng(7);
     std::uniform_real_distribution<float> ux(2.f, 30.f), uy(-6.f, 6.f), uz(0.f, 3.f);
     auto cloud = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();

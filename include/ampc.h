@@ -137,6 +137,46 @@ int ampc_cloud_index_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int3
                          void *stream);
 /* number of points held for (scene, kind) after the NaN filter (synchronises) */
 int ampc_cloud_count(ampc_handle *h, int32_t scene, int32_t kind, int32_t *n_out);
+/* copy the cloud of (scene, kind) back to the host as 16-byte float records (x, y, z, pad), in
+ * index order: what KDTreeTwo::GetPointCloud().pts holds (include/kd_tree_two.h:134-136; read by
+ * the key-frame outlier step, src/FrameKDMap.cpp:462-464).  Synchronises. */
+int ampc_cloud_get(ampc_handle *h, int32_t scene, int32_t kind, void *xyz16_out, int32_t max_points,
+                   int32_t *n_out);
+
+/* ---- depth image -> both clouds: replaces FrameKDMap::ProcessDepth + BuildEdgeCloud
+ * (src/FrameKDMap.cpp:76-130,176-214, incl. cv::resize / cv::erode / cv::Canny) followed by
+ * the two InitializeNew calls of AddVertex (:44-47), for n_scenes depth images at once.
+ * ampc_camera mirrors the perception block of config/mpc_parameters.yaml:58-66; fx..cy are the
+ * full-resolution intrinsics (the library divides by resize_scale as the constructor does,
+ * src/FrameKDMap.cpp:21-24).  Defaults = the shipped yaml. */
+typedef struct ampc_camera {
+    double fx, fy, cx, cy;
+    double resize_scale; /* mParamDepthScale, >= 1 */
+    double pixel2meter;
+    double depth_min, depth_max; /* metres */
+} ampc_camera;
+int ampc_set_camera(ampc_handle *h, const ampc_camera *cam);
+#define AMPC_DEPTH_F32 0 /* CV_32FC1 (the simulator's metres) */
+#define AMPC_DEPTH_U16 1 /* CV_16UC1 */
+/*   depth         n_scenes images, rows x cols, row_stride_bytes between rows,
+ *                 image_stride_bytes between images (ignored for n_scenes == 1)
+ *   T_obstacle    n_scenes x 16 doubles, row-major 4x4 camera->world transform applied to the
+ *                 Obstacle points: mat4Twb * mParamTbc (:117-119)
+ *   T_edge        same for the Edge points; the reference applies mCurFrame.Twc * mParamTbc,
+ *                 i.e. the PREVIOUS frame's Twc times Tbc once more (:208-209) -- the caller
+ *                 decides; NULL = T_obstacle
+ * Fills the Obstacle slot (and the Edge slot when the handle has Edge capacity) of scenes
+ * first_scene.. and builds their indices.  The Edge cloud of a scene whose Obstacle cloud came
+ * out empty is empty (:125-127).  Needs rows/scale * cols/scale <= max_points; returns
+ * AMPC_ERR_CAPACITY if an Edge cloud outgrew max_edge_points (it is truncated). */
+int ampc_depth_set_batch(ampc_handle *h, int32_t first_scene, int32_t n_scenes, const void *depth_host,
+                         int32_t dtype, int32_t rows, int32_t cols, int64_t row_stride_bytes,
+                         int64_t image_stride_bytes, const double *T_obstacle, const double *T_edge);
+/* same with the images and transforms already in device memory; async on stream */
+int ampc_depth_set_batch_dev(ampc_handle *h, int32_t first_scene, int32_t n_scenes, const void *depth_dev,
+                             int32_t dtype, int32_t rows, int32_t cols, int64_t row_stride_bytes,
+                             int64_t image_stride_bytes, const double *T_obstacle_dev,
+                             const double *T_edge_dev, void *stream);
 
 /* ---- k-NN: replaces KDTreeTwo::SearchForNearest (include/kd_tree_two.h:108-133)
  * behind FrameKDMap::QueryNearest's current-frame path (src/FrameKDMap.cpp:254-275,
