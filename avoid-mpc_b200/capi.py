@@ -11,7 +11,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libampc.so")
+# AMPC_LIB: developer knob to A/B another build of the same library (e.g. lib/variants/*.so)
+LIB_PATH = os.environ.get("AMPC_LIB") or os.path.join(_HERE, "lib", "libampc.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, 1, 2, 3, 4

@@ -81,6 +81,7 @@ struct ampc_handle {
     std::string err;
     int solve_smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int solve_warps = 2;
+    int solve_smem_pad = 0; // AMPC_SOLVE_SMEM_PAD: extra dynamic shared memory per CTA (occupancy experiments)
     int knn_smem_set = 0;
     bool index_smem_set = false;
     // optional per-kernel timing of ampc_round_batch_dev (CUDA events on the caller's stream)
@@ -456,7 +457,7 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
 template <int W>
 int launch_solve_w(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
                    cudaStream_t st, const int32_t *active) {
-    const size_t smem = solve_smem_bytes(h->cfg.N, W);
+    const size_t smem = solve_smem_bytes(h->cfg.N, W) + (size_t)h->solve_smem_pad;
     if (smem > 227 * 1024)
         return fail(h, AMPC_ERR_UNSUPPORTED, "horizon too long for the per-warp shared-memory layout");
     if ((int)smem > h->solve_smem_set[W]) {
@@ -555,6 +556,10 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
     if (const char *e = std::getenv("AMPC_SOLVE_WARPS")) { // tuning knob: 1, 2, 4 or 8
         const int v = std::atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) h->solve_warps = v;
+    }
+    if (const char *e = std::getenv("AMPC_SOLVE_SMEM_PAD")) {
+        const int v = std::atoi(e);
+        if (v > 0 && v < 200 * 1024) h->solve_smem_pad = v & ~15;
     }
     // defaults of the reference constructor (src/HighLvlMpc.cpp:11-14,53-58)
     const double w0[25] = {100, 100, 100, 300, 1, 1, 1, 0., 0., 0., 0.0, 10, 10,

@@ -46,6 +46,12 @@ __device__ __forceinline__ float depth_src_inv(const DepthGeom &g, const unsigne
     const double dd = (double)d;
     if (dd < g.dmin || dd > g.dmax)
         return 0.f;
+    // float(1. / double(d)) == RN_float(1 / d): d * m for a float d (24 bits) and a float rounding
+    // boundary m (25 bits) is a 49-bit integer, so 1 / d is either a boundary exactly or at least
+    // 2^-49 (relative) away from one -- the 2^-53 error of the double quotient cannot move it
+    // across.  One correctly rounded float reciprocal replaces the double division.
+    if (fabsf(d) > 1e-18f && fabsf(d) < 1e18f)
+        return __frcp_rn(d);
     return (float)(1.0 / dd);
 }
 

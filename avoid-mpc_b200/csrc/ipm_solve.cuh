@@ -859,7 +859,10 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+#ifndef AMPC_SOLVE_MIN_BLOCKS
+#define AMPC_SOLVE_MIN_BLOCKS 1 // occupancy is bounded by the ~246 registers the Riccati blocks need
+#endif
+__global__ void __launch_bounds__(WARPS * 32, AMPC_SOLVE_MIN_BLOCKS)
 ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double *__restrict__ prefix,
                  double *__restrict__ w_inout, SolveOut *__restrict__ info,
                  const int32_t *__restrict__ active /* nullable: instances with 0 are skipped */) {
