@@ -18,6 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 SOLVE_CONVERGED, SOLVE_MAX_ITER, SOLVE_STALLED, SOLVE_NUMERIC = 0, 1, 2, 3
 CLOUD_OBSTACLE, CLOUD_EDGE = 0, 1
+LAYOUT_UNORGANISED, LAYOUT_SORT = 0, -1  # ampc_cloud_set_layout; a value >= 8 is an image row pitch
 
 # every symbol include/ampc.h declares (tests check the library exports all of them)
 SYMBOLS = [
@@ -254,6 +255,8 @@ class Handle:
                                                  Pn * 16, stream))
 
     def cloud_set_layout(self, row_width, kind=CLOUD_OBSTACLE):
+        """row_width >= 8: organised cloud (image row pitch); LAYOUT_UNORGANISED; LAYOUT_SORT: arbitrary
+        storage order, index built over a Morton-bucketed copy."""
         self._ck(self.L.ampc_cloud_set_layout(self.h, kind, row_width))
 
     def cloud_count(self, scene, kind=CLOUD_OBSTACLE):

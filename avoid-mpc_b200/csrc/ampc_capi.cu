@@ -62,9 +62,11 @@ struct ampc_handle {
     cudaStream_t stream = nullptr;
     // clouds: [kind] slot buffers + counts
     DevBuf cloud[2], counts[2], boxes[2], nan_flags[2];
+    DevBuf sorted[2]; // Morton-bucketed copies for layout -1 (allocated on first use)
+    bool sort_smem_set = false;
     int slot_points[2] = {0, 0};
     int slot_tiles[2] = {0, 0};
-    int row_w[2] = {0, 0}; // organised-cloud row pitch hint per kind for the next cloud_set (0: unorganised)
+    int row_w[2] = {0, 0}; // layout hint per kind for the next cloud_set: 0 unorganised, > 0 row pitch, -1 Morton-bucketed
     DevBuf layout[2];      // per scene: the row pitch its tiles were built with
     DevBuf raw_stage; // staging for stride != 16 uploads
     // depth image -> clouds
@@ -390,6 +392,7 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     }
     KnnParams P{};
     P.clouds = h->cloud[kind].as<float4>();
+    P.sorted = h->sorted[kind].as<float4>();
     P.boxes = h->boxes[kind].as<float4>();
     P.counts = h->counts[kind].as<int32_t>();
     P.slot_points = h->slot_points[kind];
@@ -428,7 +431,9 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     return AMPC_OK;
 }
 
-int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaStream_t st) {
+// sort_mode: the scenes were given layout -1 -> after the NaN filter, bucket a copy of each
+// cloud by Morton cell and build the tile boxes over the copy
+int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaStream_t st, bool sort_mode = false) {
     int slot;
     int rc = prof_begin(h, SEC_INDEX, st, &slot);
     if (rc) return rc;
@@ -441,6 +446,10 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
         h->index_smem_set = true;
     }
     if (parts > 65535) parts = 65535;
+    if (sort_mode && !h->sorted[kind].p) {
+        CK(cudaStreamSynchronize(st));
+        CK(h->sorted[kind].reserve((size_t)h->cfg.max_scenes * h->slot_points[kind] * 16));
+    }
     cloud_index_kernel<<<dim3(n_scenes, parts), KI_THREADS, 2 * KI_BAND_BYTES, st>>>(
         h->cloud[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
         h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->layout[kind].as<int32_t>(), first_scene);
@@ -451,6 +460,24 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
         h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->layout[kind].as<int32_t>(), first_scene);
     h->launches++;
     CK(cudaGetLastError());
+    if (sort_mode) {
+        if (!h->sort_smem_set) {
+            CK(cudaFuncSetAttribute(cloud_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM_BYTES));
+            h->sort_smem_set = true;
+        }
+        cloud_sort_kernel<<<n_scenes, KM_THREADS, KM_SMEM_BYTES, st>>>(
+            h->cloud[kind].as<float4>(), h->sorted[kind].as<float4>(), h->boxes[kind].as<float4>(),
+            h->counts[kind].as<int32_t>(), h->layout[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind],
+            first_scene);
+        h->launches++;
+        CK(cudaGetLastError());
+        // tile boxes over the bucketed copy replace the ones of the original order
+        cloud_index_kernel<<<dim3(n_scenes, parts), KI_THREADS, 2 * KI_BAND_BYTES, st>>>(
+            h->sorted[kind].as<float4>(), h->boxes[kind].as<float4>(), h->counts[kind].as<int32_t>(),
+            h->nan_flags[kind].as<int32_t>(), h->slot_points[kind], h->slot_tiles[kind], h->layout[kind].as<int32_t>(), first_scene);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     return prof_end(h, slot, st);
 }
 
@@ -622,7 +649,8 @@ void ampc_destroy(ampc_handle *h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream)
         cudaStreamSynchronize(h->stream);
-    DevBuf *all[] = {&h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
+    DevBuf *all[] = {&h->sorted[0], &h->sorted[1], &h->layout[0], &h->layout[1], &h->depth_stage, &h->depth_T, &h->depth_tab,
+                     &h->depth_scratch, &h->depth_flag, &h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
                      &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
@@ -760,7 +788,7 @@ static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_sce
     }
     rc = set_layout(h, kind, first_scene, n_scenes, st);
     if (rc) return rc;
-    return launch_index(h, kind, first_scene, n_scenes, st);
+    return launch_index(h, kind, first_scene, n_scenes, st, h->row_w[kind] == AMPC_LAYOUT_SORT);
 }
 
 int ampc_cloud_set(ampc_handle *h, int32_t scene, int32_t kind, const void *xyz_host, int32_t n,
@@ -792,8 +820,8 @@ int ampc_cloud_set_layout(ampc_handle *h, int32_t kind, int32_t row_width) {
     if (!h) return AMPC_ERR_INVALID;
     int rc = check_kind(h, kind);
     if (rc) return rc;
-    if (row_width != 0 && row_width < 8)
-        return fail(h, AMPC_ERR_INVALID, "row_width must be 0 (unorganised) or >= 8");
+    if (row_width != AMPC_LAYOUT_UNORGANISED && row_width != AMPC_LAYOUT_SORT && row_width < 8)
+        return fail(h, AMPC_ERR_INVALID, "row_width must be AMPC_LAYOUT_UNORGANISED (0), AMPC_LAYOUT_SORT (-1) or >= 8");
     h->row_w[kind] = row_width;
     return AMPC_OK;
 }
@@ -943,7 +971,7 @@ int ampc_cloud_index_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int3
     CK(cudaSetDevice(h->cfg.device));
     rc = set_layout(h, kind, first_scene, n_scenes, (cudaStream_t)stream);
     if (rc) return rc;
-    return launch_index(h, kind, first_scene, n_scenes, (cudaStream_t)stream);
+    return launch_index(h, kind, first_scene, n_scenes, (cudaStream_t)stream, h->row_w[kind] == AMPC_LAYOUT_SORT);
 }
 
 // ---- depth image -> Obstacle + Edge cloud (FrameKDMap::ProcessDepth, src/FrameKDMap.cpp:90-130)

@@ -385,7 +385,44 @@ __device__ __noinline__ double eval_value(const WarpCtx &w, double eps, const bo
 // redundantly in every lane.  Returns false if a pivot of S is not positive (the reduced
 // Hessian has the wrong inertia) -> the caller regularises.  Also returns the dual
 // infeasibility |r_k + G'lam_{k+1} - zl + zu|_inf.
-__device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, double *e_dual_out) {
+// Dual infeasibility |grad_U L|_inf of the current iterate: the costate recursion
+// lam_k = q_k + Phi' lam_{k+1}, grad_{U_k} L = r_k - zl_k + zu_k + Gam' lam_{k+1}, chain by
+// chain (lane -> chain (lane >> 2) & 3, computed redundantly).  This is all the convergence
+// test and the mu rule need, so they run BEFORE the Newton system is factored: one Riccati
+// sweep per iteration whether or not mu changes, none for the final test.
+__device__ __noinline__ double adjoint_dual_inf(const WarpCtx &w) {
+    const SolveConsts &c = *w.c;
+    const int N = c.N;
+    const double *s = w.s;
+    const WarpLayout &L = w.L;
+    const int ci = (w.lane & 15) >> 2;
+    const Chain fi = load_chain(c.Phi, c.Gam, ci);
+    const int si0 = chain_state(ci, 0), si1 = chain_state(ci, 1), si2 = chain_state(ci, 2);
+    const int q1 = ci < 3 ? si1 : si0, q2 = ci < 3 ? si2 : si0; // padding reads a valid slot,
+    const double m_ax = ci < 3 ? 1.0 : 0.0;                     // masked to zero
+    double lv[3];
+    lv[0] = s[L.q + 10 * N + si0];
+    lv[1] = m_ax * s[L.q + 10 * N + q1];
+    lv[2] = m_ax * s[L.q + 10 * N + q2];
+    double e_dual = 0.0;
+#pragma unroll 2
+    for (int k = N - 1; k >= 0; --k) {
+        const double guk = s[L.r + 4 * k + ci] - s[L.zl + 4 * k + ci] + s[L.zu + 4 * k + ci];
+        const double gu = guk + fi.g1 * lv[0] + fi.g2 * lv[1] + fi.g3 * lv[2];
+        e_dual = fmax(e_dual, fabs(gu));
+        if (k == 0)
+            break;
+        const double qk0 = s[L.q + 10 * k + si0];
+        const double qk1 = m_ax * s[L.q + 10 * k + q1];
+        const double qk2 = m_ax * s[L.q + 10 * k + q2];
+        double fl[3];
+        chain_FT(fi, lv, fl);
+        lv[0] = qk0 + fl[0], lv[1] = qk1 + fl[1], lv[2] = qk2 + fl[2];
+    }
+    return warp_max(e_dual);
+}
+
+__device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta) {
     const SolveConsts &c = *w.c;
     const int N = c.N;
     double *s = w.s;
@@ -406,9 +443,9 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, do
     const double q22c = real && diag ? 2.0 * qp[si2] + delta : 0.0;
     const int q1 = ci < 3 ? si1 : si0, q2 = ci < 3 ? si2 : si0; // padding reads a valid slot,
     const double m_ax = ci < 3 ? 1.0 : 0.0;                     // masked to zero
-    // terminal: P_N = diag(2 Q_goal) + delta, p_N = lam_N = q_N
+    // terminal: P_N = diag(2 Q_goal) + delta, p_N = q_N
     double P[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double pv[3], lv[3];
+    double pv[3];
     if (diag) {
         P[0] = 2.0 * qg[si0] + delta;
         if (ci < 3) {
@@ -419,13 +456,10 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, do
     pv[0] = s[L.q + 10 * N + si0];
     pv[1] = m_ax * s[L.q + 10 * N + q1];
     pv[2] = m_ax * s[L.q + 10 * N + q2];
-    lv[0] = pv[0], lv[1] = pv[1], lv[2] = pv[2];
-    double e_dual = 0.0;
     bool ok = true;
     for (int k = N - 1; k >= 0; --k) {
         // operands from shared memory first (latency overlaps the products)
         const double rdk = s[L.rdiag + 4 * k + ci], rtk = s[L.rt + 4 * k + ci];
-        const double guk = s[L.r + 4 * k + ci] - s[L.zl + 4 * k + ci] + s[L.zu + 4 * k + ci];
         double Qb0 = q00c, Qb1 = 0.0, Qb3 = 0.0, Qb4 = q11c, qk0 = 0.0, qk1 = 0.0, qk2 = 0.0;
         if (k > 0) {
             const double *Hc = s + L.Hc + 21 * (k - 1);
@@ -457,8 +491,6 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, do
             A[6 + b] = fi.c2 * M[b] + fi.c3 * M[3 + b] + fi.c4 * M[6 + b];
         }
         const double bi = rtk + fi.g1 * pv[0] + fi.g2 * pv[1] + fi.g3 * pv[2];
-        const double gu = guk + fi.g1 * lv[0] + fi.g2 * lv[1] + fi.g3 * lv[2];
-        e_dual = fmax(e_dual, m_diag * fabs(gu));
         // (2) S = L D L' (3x3 for the axes; yaw is a decoupled scalar), every lane redundantly
         const double S00 = __shfl_sync(AMPC_FULL_MASK, Sij, 0), S10 = __shfl_sync(AMPC_FULL_MASK, Sij, 4);
         const double S20 = __shfl_sync(AMPC_FULL_MASK, Sij, 8), S11 = __shfl_sync(AMPC_FULL_MASK, Sij, 5);
@@ -522,8 +554,7 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, do
         }
         if (w.lane == 15)
             s[L.Kg + 48 * k + 36 + 9] = -bm[0] * i3; // the never-written slots stay zero (cleared at start)
-        // (4) P^(ij) <- Q^(ij) + A - Bm^(i) Y ;  p^(i) <- q^(i) + F_i' p^(i) + Bm^(i) kff ;
-        //     lam^(i) <- q^(i) + F_i' lam^(i)
+        // (4) P^(ij) <- Q^(ij) + A - Bm^(i) Y ;  p^(i) <- q^(i) + F_i' p^(i) + Bm^(i) kff
         const double yy = yaw ? i3 : 0.0; // yaw block: - bm bm' / S33
 #pragma unroll
         for (int a = 0; a < 3; ++a)
@@ -532,21 +563,17 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta, do
                 P[3 * a + b] = A[3 * a + b] - (Bi[a][0] * Y[0][b] + Bi[a][1] * Y[1][b] + Bi[a][2] * Y[2][b]) -
                                yy * bm[a] * bm[b];
         P[0] += Qb0, P[1] += Qb1, P[3] += Qb3, P[4] += Qb4, P[8] += q22c;
-        double fp[3], fl[3];
+        double fp[3];
         chain_FT(fi, pv, fp);
-        chain_FT(fi, lv, fl);
         const double kq[3] = {qk0, qk1, qk2};
         const double ky = yaw ? kff3 : 0.0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             pv[a] = kq[a] + fp[a] + Bi[a][0] * kff0 + Bi[a][1] * kff1 + Bi[a][2] * kff2 + ky * bm[a];
-            lv[a] = kq[a] + fl[a];
         }
     }
     __syncwarp();
-    ok = __all_sync(AMPC_FULL_MASK, ok);
-    *e_dual_out = warp_max(e_dual);
-    return ok;
+    return __all_sync(AMPC_FULL_MASK, ok);
 }
 
 // forward sweep: du_k = K_k dx_k + kff_k, dx_{k+1} = Phi dx_k + Gam du_k, dx_0 = 0.
@@ -677,12 +704,17 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             __syncthreads();
         double eps = 0.0, f = 0.0, c_mu = 0.0, delta = 0.0;
         bool stop = false;
-        // pass 0: evaluate, sweep, test convergence, update mu (IPOPT eq. (7)); if mu changed the
-        // smoothing and the barrier gradient changed, so pass 1 evaluates and sweeps again
+        // pass 0: evaluate, test convergence, update mu (IPOPT eq. (7)); if mu changed, the
+        // barrier terms changed, and so did the smoothing unless it sits at its floor: pass 1
+        // refreshes what depends on them.  Then ONE Newton system per iteration.
+        double eps_at = -1.0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             eps = fmax(c.eps_min, c.eps_scale * mu);
-            f = eval_cost<true, false>(w, eps);
+            if (eps != eps_at) {
+                f = eval_cost<true, false>(w, eps);
+                eps_at = eps;
+            }
             double ec = 0.0, cm = 0.0;
 #pragma unroll 1
             for (int e = lane; e < nu; e += 32) {
@@ -696,26 +728,9 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
                 s[L.rt + e] = s[L.r + e] - mu * isl + mu * isu;
             }
             __syncwarp();
-            // Newton system with inertia correction (IPOPT Algorithm IC schedule); the adjoint /
-            // dual-infeasibility part of the sweep does not depend on delta
-            delta = 0.0;
-            int ntry = 0;
-            double ed = 0.0;
-#pragma unroll 1
-            while (!riccati_backward(w, delta, &ed)) {
-                if (delta == 0.0)
-                    delta = (delta_last == 0.0) ? 1e-4 : fmax(1e-20, delta_last / 3.0);
-                else
-                    delta *= (delta_last == 0.0) ? 100.0 : 8.0;
-                if (++ntry > 60 || delta > 1e40) {
-                    status = 3;
-                    stop = true;
-                    break;
-                }
-            }
-            if (stop || pass == 1)
+            if (pass == 1)
                 break;
-            e_dual = ed;
+            e_dual = adjoint_dual_inf(w);
             e_compl = warp_max(ec);
             c_mu = warp_max(cm);
             if (!(f == f) || !(e_dual == e_dual)) {
@@ -746,6 +761,24 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             }
             if (!mu_changed)
                 break;
+        }
+        if (stop)
+            break;
+        // Newton system with inertia correction (IPOPT Algorithm IC schedule)
+        {
+            int ntry = 0;
+#pragma unroll 1
+            while (!riccati_backward(w, delta)) {
+                if (delta == 0.0)
+                    delta = (delta_last == 0.0) ? 1e-4 : fmax(1e-20, delta_last / 3.0);
+                else
+                    delta *= (delta_last == 0.0) ? 100.0 : 8.0;
+                if (++ntry > 60 || delta > 1e40) {
+                    status = 3;
+                    stop = true;
+                    break;
+                }
+            }
         }
         if (stop)
             break;

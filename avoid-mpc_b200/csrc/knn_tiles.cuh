@@ -90,11 +90,13 @@ __host__ __device__ inline int64_t tile_capacity(int64_t max_points) {
 
 struct KnnParams {
     const float4 *clouds;    // slot s at clouds + s*slot_points
+    const float4 *sorted;    // Morton-bucketed copies (x, y, z, original index) of the scenes whose layout is -1
     const float4 *boxes;     // slot s at boxes + s*slot_tiles*2 (two float4 per tile)
     const int32_t *counts;   // points held in each slot (after the NaN filter)
     int64_t slot_points;
     int64_t slot_tiles;
-    const int32_t *layout;   // per scene: 0 = unorganised cloud; >0 = row pitch for 8x8 patch tiles
+    const int32_t *layout;   // per scene: 0 = unorganised cloud; >0 = row pitch for 8x8 patch tiles;
+                             // -1 = tiles over the Morton-bucketed copy (cloud_sort_kernel)
     const int32_t *scene_of; // [B] or nullptr (identity)
     const int32_t *active;   // [B] or nullptr: instances with 0 are skipped (outputs untouched)
     const double *queries;   // [B][Q][3]
@@ -369,6 +371,138 @@ cloud_compact_kernel(float4 *clouds, float4 *boxes, int32_t *counts, int32_t *na
     }
 }
 
+// ---- Morton bucketing of an unorganised cloud (layout -1) --------------------------------
+// A cloud in arbitrary storage order gives 64-record tiles whose boxes span the scene, and
+// the search degenerates to a full scan.  For such clouds the index is built over a COPY of
+// the cloud bucketed by the 15-bit Morton code of each point (5 bits per axis of the scene's
+// bounding box): a counting sort, one CTA per scene, histogram and running offsets in shared
+// memory (32768 cells x 4 B = 128 KB).  The copy keeps the original index in the pad word
+// (x, y, z, index), so neighbour indices remain the reference's indices; the order inside a
+// cell is whatever the atomics produce, which cannot matter: the result list is ordered by
+// (dist2, index) and every box is valid for whatever 64 records its tile holds.
+// This is the flat (one level of 64-point leaves) form of a Morton-ordered linear BVH.
+constexpr int KM_THREADS = 1024;
+constexpr int KM_BITS = 5;
+constexpr int KM_CELLS = 1 << (3 * KM_BITS);
+constexpr int KM_SMEM_BYTES = KM_CELLS * 4;
+
+__device__ __forceinline__ uint32_t morton_spread(uint32_t v) { // bit i of v (v < 1024) -> bit 3i
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+struct MortonGrid {
+    float lx, ly, lz, sx, sy, sz;
+    // NaN / inf coordinates and degenerate extents fall into cell 0 of that axis
+    // (fmaxf(NaN, 0) = 0); every record gets SOME cell, which is all correctness needs
+    __device__ __forceinline__ uint32_t cell(float4 p) const {
+        const float top = (float)((1 << KM_BITS) - 1);
+        const uint32_t cx = (uint32_t)fminf(fmaxf((p.x - lx) * sx, 0.f), top);
+        const uint32_t cy = (uint32_t)fminf(fmaxf((p.y - ly) * sy, 0.f), top);
+        const uint32_t cz = (uint32_t)fminf(fmaxf((p.z - lz) * sz, 0.f), top);
+        return morton_spread(cx) | (morton_spread(cy) << 1) | (morton_spread(cz) << 2);
+    }
+};
+
+// boxes: the linear-tile boxes of the ORIGINAL cloud (cloud_index_kernel ran over it just
+// before, which also applied the NaN filter); they are only reduced to the scene's box here.
+__global__ void __launch_bounds__(KM_THREADS, 1)
+cloud_sort_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ sorted,
+                  const float4 *__restrict__ boxes, const int32_t *__restrict__ counts,
+                  const int32_t *__restrict__ layout, int64_t slot_points, int64_t slot_tiles,
+                  int first_scene) {
+    extern __shared__ __align__(16) uint32_t km_hist[]; // KM_CELLS counters, then running offsets
+    __shared__ float sBox[6][KM_THREADS / 32];
+    __shared__ uint32_t sWarpTotal[KM_THREADS / 32];
+    const int scene = first_scene + blockIdx.x;
+    if (layout[scene] != -1)
+        return;
+    const int n = counts[scene];
+    const float4 *c = clouds + (int64_t)scene * slot_points;
+    float4 *s = sorted + (int64_t)scene * slot_points;
+    const float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = KM_THREADS / 32;
+
+    // scene box = union of the tile boxes (empty tiles hold +inf / -inf and drop out)
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const int n_tiles = (n + KT_TILE - 1) / KT_TILE;
+    for (int t = tid; t < n_tiles; t += KM_THREADS) {
+        const float4 a = bx[2 * t], h = bx[2 * t + 1];
+        lo[0] = fminf(lo[0], a.x), lo[1] = fminf(lo[1], a.y), lo[2] = fminf(lo[2], a.z);
+        hi[0] = fmaxf(hi[0], a.w), hi[1] = fmaxf(hi[1], h.x), hi[2] = fmaxf(hi[2], h.y);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float l = warp_fmin(lo[a]), h = warp_fmax(hi[a]);
+        if (lane == 0) {
+            sBox[a][warp] = l;
+            sBox[3 + a][warp] = h;
+        }
+    }
+    for (int i = tid; i < KM_CELLS; i += KM_THREADS)
+        km_hist[i] = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = warp_fmin(sBox[a][lane]);
+        hi[a] = warp_fmax(sBox[3 + a][lane]);
+    }
+    MortonGrid g;
+    {
+        const float cells = (float)(1 << KM_BITS);
+        const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        g.lx = lo[0], g.ly = lo[1], g.lz = lo[2];
+        g.sx = (ex > 0.f && ex < INFINITY) ? cells / ex : 0.f;
+        g.sy = (ey > 0.f && ey < INFINITY) ? cells / ey : 0.f;
+        g.sz = (ez > 0.f && ez < INFINITY) ? cells / ez : 0.f;
+    }
+    // pass 1: cell histogram
+#pragma unroll 4
+    for (int i = tid; i < n; i += KM_THREADS)
+        atomicAdd(&km_hist[g.cell(knn_ldg(c + i))], 1u);
+    __syncthreads();
+    // exclusive scan of the 32768 counters: warp w owns cells [1024 w, 1024 w + 1024)
+    {
+        uint32_t *mine = km_hist + warp * (KM_CELLS / NW);
+        uint32_t total = 0;
+        for (int ch = 0; ch < KM_CELLS / NW; ch += 32)
+            total += mine[ch + lane];
+        total = __reduce_add_sync(AMPC_FULL_MASK, total);
+        if (lane == 0)
+            sWarpTotal[warp] = total;
+        __syncthreads();
+        uint32_t v = sWarpTotal[lane], incl = v; // NW == 32: lane l holds warp l's total
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(AMPC_FULL_MASK, incl, o);
+            if (lane >= o) incl += u;
+        }
+        uint32_t running = __shfl_sync(AMPC_FULL_MASK, incl - v, warp); // cells before this warp's range
+        for (int ch = 0; ch < KM_CELLS / NW; ch += 32) {
+            const uint32_t cnt = mine[ch + lane];
+            uint32_t inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(AMPC_FULL_MASK, inc, o);
+                if (lane >= o) inc += u;
+            }
+            mine[ch + lane] = running + inc - cnt;
+            running += __shfl_sync(AMPC_FULL_MASK, inc, 31);
+        }
+    }
+    __syncthreads();
+    // pass 2: scatter (x, y, z, original index) to the cell's next free slot
+#pragma unroll 4
+    for (int i = tid; i < n; i += KM_THREADS) {
+        const float4 p = knn_ldg(c + i);
+        const uint32_t slot = atomicAdd(&km_hist[g.cell(p)], 1u);
+        s[slot] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    }
+}
+
 // ---- register-resident sorted top-k list: lane j holds entry j -----------------
 struct TopK {
     double d;
@@ -451,27 +585,31 @@ __device__ __noinline__ void merge_dense_tile(TopK &e, int k, double d0, uint32_
     e.i = lane < k ? mi : 0xffffffffu;
 }
 
-// scan one tile: exact distances of its (up to) 64 points, candidates into the list
+// scan one tile: exact distances of its (up to) 64 points, candidates into the list.
+// by_w: `cloud` is a Morton-bucketed copy whose pad word holds the point's original index.
 __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const TileGeom &g, int tile,
                                           double qx, double qy, double qz, TopK &e, double &kth, int k,
-                                          int lane) {
+                                          int lane, bool by_w) {
     int i0, i1;
     g.points2(tile, lane, n, i0, i1);
     double d0 = INFINITY, d1 = INFINITY;
+    uint32_t id0 = (uint32_t)i0, id1 = (uint32_t)i1;
     if (i0 >= 0) {
         const float4 p = knn_ldg(cloud + i0);
         d0 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
+        if (by_w) id0 = (uint32_t)__float_as_int(p.w);
     }
     if (i1 >= 0) {
         const float4 p = knn_ldg(cloud + i1);
         d1 = knn_dist2(qx, qy, qz, p.x, p.y, p.z);
+        if (by_w) id1 = (uint32_t)__float_as_int(p.w);
     }
     const bool c0 = i0 >= 0 && d0 <= kth, c1 = i1 >= 0 && d1 <= kth;
     unsigned m0 = __ballot_sync(AMPC_FULL_MASK, c0);
     unsigned m1 = __ballot_sync(AMPC_FULL_MASK, c1);
     if (k <= 16 && __popc(m0) + __popc(m1) >= KS_DENSE) {
-        merge_dense_tile(e, k, c0 ? d0 : INFINITY, c0 ? (uint32_t)i0 : 0xffffffffu, c1 ? d1 : INFINITY,
-                         c1 ? (uint32_t)i1 : 0xffffffffu, lane);
+        merge_dense_tile(e, k, c0 ? d0 : INFINITY, c0 ? id0 : 0xffffffffu, c1 ? d1 : INFINITY,
+                         c1 ? id1 : 0xffffffffu, lane);
         kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
         return;
     }
@@ -480,7 +618,7 @@ __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const Tile
         m0 &= m0 - 1;
         const double d = __shfl_sync(AMPC_FULL_MASK, d0, src);
         if (d <= kth) {
-            topk_insert(e, k, d, (uint32_t)__shfl_sync(AMPC_FULL_MASK, i0, src), lane);
+            topk_insert(e, k, d, __shfl_sync(AMPC_FULL_MASK, id0, src), lane);
             kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
         }
     }
@@ -489,7 +627,7 @@ __device__ __forceinline__ void scan_tile(const float4 *cloud, int n, const Tile
         m1 &= m1 - 1;
         const double d = __shfl_sync(AMPC_FULL_MASK, d1, src);
         if (d <= kth) {
-            topk_insert(e, k, d, (uint32_t)__shfl_sync(AMPC_FULL_MASK, i1, src), lane);
+            topk_insert(e, k, d, __shfl_sync(AMPC_FULL_MASK, id1, src), lane);
             kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
         }
     }
@@ -570,7 +708,10 @@ knn_search_kernel(const KnnParams P) {
     const float4 *boxes = P.boxes + (int64_t)scene * P.slot_tiles * 2;
     const double *qp = P.queries + ((int64_t)b * P.Q + q) * 3;
     const double qx = qp[0], qy = qp[1], qz = qp[2];
-    const TileGeom g(n, P.layout[scene]);
+    const int lay = P.layout[scene];
+    const bool by_w = lay < 0; // tiles over the Morton-bucketed copy; indices come from its pad word
+    const float4 *tsrc = by_w ? P.sorted + (int64_t)scene * P.slot_points : cloud;
+    const TileGeom g(n, lay);
     const int n_tiles = g.n_tiles;
     const int per = (n_tiles + P.segs - 1) / P.segs;
     const int t_begin = seg * per, t_end = min(n_tiles, t_begin + per);
@@ -629,7 +770,7 @@ knn_search_kernel(const KnnParams P) {
                 break;
             const int j = cand[best_c];
             double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
-            scan_tile(cloud, n, g, c0 + j, qx, qy, qz, e, kth, k, lane);
+            scan_tile(tsrc, n, g, c0 + j, qx, qy, qz, e, kth, k, lane, by_w);
             bound = fmin(bound, kth);
             __syncwarp(); // every lane has finished reading lbuf for this pick
             if (lane == 0)
@@ -648,7 +789,7 @@ knn_search_kernel(const KnnParams P) {
                 if (lbj <= bound) { // the bound may have tightened since the ballot
                     const int jj = __shfl_sync(AMPC_FULL_MASK, j, src);
                     double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
-                    scan_tile(cloud, n, g, c0 + jj, qx, qy, qz, e, kth, k, lane);
+                    scan_tile(tsrc, n, g, c0 + jj, qx, qy, qz, e, kth, k, lane, by_w);
                     bound = fmin(bound, kth);
                 }
             }

@@ -83,6 +83,10 @@ private:
                 throw std::runtime_error(std::string("KDTreeTwo(GPU): ") + ampc_last_error(nullptr));
             h.reset(raw, ampc_destroy);
         }
+        // InitializeNew accepts points in any order (kd_tree_two.h:88-106): larger clouds are indexed
+        // over a Morton-bucketed copy; indices stay those of cloud.pts
+        if (ampc_cloud_set_layout(h.get(), AMPC_CLOUD_OBSTACLE, n >= 8192 ? AMPC_LAYOUT_SORT : AMPC_LAYOUT_UNORGANISED) != AMPC_OK)
+            throw std::runtime_error(std::string("KDTreeTwo(GPU): ") + ampc_last_error(h.get()));
         if (ampc_cloud_set(h.get(), 0, AMPC_CLOUD_OBSTACLE, cloud.pts.data(), n, 16) != AMPC_OK)
             throw std::runtime_error(std::string("KDTreeTwo(GPU): ") + ampc_last_error(h.get()));
     }

@@ -571,7 +571,7 @@ def run_knn_sweep(args):
         hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         hbm_peak = 6650.0
-    rows = []
+    rows, shuffled = [], []
     for npts in (10000, 20000, 50000, 100000, 200000, 500000, 1000000):
         B = int(min(4096, max(8, 2e9 // (16 * npts))))
         ids = list(range(B))
@@ -605,9 +605,41 @@ def run_knn_sweep(args):
                      "as_laid_out_16B_index_GBps": B * 16 * npts / (t_i * 1e-3) / 1e9,
                      "scene_rounds_per_s": B / ((t_i + t_s) * 1e-3)})
         h.close()
+        # the same points in arbitrary storage order (what KDTreeTwo::InitializeNew may be given):
+        # 64-consecutive-record tiles (AMPC_LAYOUT_UNORGANISED) against the Morton-bucketed copy
+        # (AMPC_LAYOUT_SORT).  Both must return the very same indices.
+        if npts in (50000, 1000000):
+            perm = torch.randperm(npts, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+            clouds = clouds[:, perm].contiguous()
+            res = {}
+            for name, lay, Bs in (("unorganised", A.capi.LAYOUT_UNORGANISED, min(B, 64)), ("sort", A.capi.LAYOUT_SORT, B)):
+                h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=Bs, max_points=npts, device=local)
+                h.cloud_set_layout(lay)
+                h.cloud_set_batch_dev(clouds[:Bs], stream=stream)
+                ti, ts = [], []
+                for it in range(2 + min(args.steps, 5)):
+                    ev[0].record()
+                    h.cloud_index_dev(0, Bs, stream=stream)
+                    ev[1].record()
+                    h.knn_dev(q[:Bs], K_NB, idx[:Bs], d2[:Bs], None, cnt[:Bs], stream=stream)
+                    ev[2].record()
+                    torch.cuda.synchronize()
+                    if it >= 2:
+                        ti.append(ev[0].elapsed_time(ev[1]))
+                        ts.append(ev[1].elapsed_time(ev[2]))
+                t_i, t_s = statistics.median(ti), statistics.median(ts)
+                res[name] = (idx[:min(B, 64)].clone(), d2[:min(B, 64)].clone())
+                shuffled.append({"npts": npts, "layout": name, "batch": Bs, "index_ms": t_i, "search_ms": t_s,
+                                 "stage_GBps": Bs * b_knn / ((t_i + t_s) * 1e-3) / 1e9,
+                                 "stage_frac": Bs * b_knn / ((t_i + t_s) * 1e-3) / 1e9 / hbm_peak,
+                                 "scene_rounds_per_s": Bs / ((t_i + t_s) * 1e-3)})
+                h.close()
+            shuffled[-1]["identical_to_unorganised"] = bool((res["sort"][0] == res["unorganised"][0]).all().item()
+                                                            and (res["sort"][1] == res["unorganised"][1]).all().item())
         del clouds
         torch.cuda.empty_cache()
-    print(json.dumps({"mode": "knn_sweep", "unit": "GB/s", "peak": hbm_peak, "Q": N_H, "K": K_NB, "rows": rows}), flush=True)
+    print(json.dumps({"mode": "knn_sweep", "unit": "GB/s", "peak": hbm_peak, "Q": N_H, "K": K_NB, "rows": rows,
+                      "shuffled_storage_order": shuffled}), flush=True)
 
 
 def main():

@@ -125,11 +125,20 @@ int ampc_cloud_set_batch(ampc_handle *h, int32_t kind, int32_t first_scene, int3
 int ampc_cloud_set_batch_dev(ampc_handle *h, int32_t kind, int32_t first_scene, int32_t n_scenes,
                              const void *xyz_dev, const int32_t *counts_host,
                              int64_t scene_stride_bytes, void *stream);
-/* Optional layout hint for the clouds of `kind`: the cloud is an ORGANISED cloud stored
- * row-major with `row_width` records per image row (the resized depth image of
- * FrameKDMap::ProcessDepth, src/FrameKDMap.cpp:106-125), so the index can use 8x8 image
- * patches as tiles.  0 (default) = unorganised.  Only pruning efficiency depends on it,
- * never the results.  Takes effect at the next cloud_set / cloud_index call. */
+/* Optional layout hint for the clouds of `kind`.  Only pruning efficiency depends on it,
+ * never the results (indices are always those of the caller's record order).  Takes effect
+ * at the next cloud_set / cloud_index call.
+ *   row_width >= 8           ORGANISED cloud stored row-major with `row_width` records per
+ *                            image row (the resized depth image of FrameKDMap::ProcessDepth,
+ *                            src/FrameKDMap.cpp:106-125): the index uses 8x8 image patches.
+ *   AMPC_LAYOUT_UNORGANISED  (default) tiles are runs of 64 consecutive records; good when the
+ *                            storage order is spatially coherent (scan lines, subsets of one).
+ *   AMPC_LAYOUT_SORT         arbitrary storage order (what KDTreeTwo::InitializeNew accepts,
+ *                            include/kd_tree_two.h:75-106): the index is built over a copy of
+ *                            the cloud bucketed by Morton cell, original indices carried along
+ *                            (costs three more passes over the cloud and a second slot buffer). */
+#define AMPC_LAYOUT_UNORGANISED 0
+#define AMPC_LAYOUT_SORT (-1)
 int ampc_cloud_set_layout(ampc_handle *h, int32_t kind, int32_t row_width);
 /* rebuild the index (NaN filter + tile boxes) of clouds already resident in the
  * handle's slots, e.g. after writing a new depth frame's points in place; async */

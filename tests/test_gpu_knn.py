@@ -129,3 +129,112 @@ def test_layout_hint_changes_nothing_but_speed(row_w):
     queries = np.stack([S.states(40 + s, Q)[1][:, :3] for s in range(3)])
     _check(h, clouds, queries, k)
     h.close()
+
+
+def _shuffled(c, seed):
+    """The same points in arbitrary storage order (what KDTreeTwo::InitializeNew may be handed)."""
+    return np.ascontiguousarray(c[np.random.default_rng(seed).permutation(len(c))])
+
+
+@pytest.mark.parametrize("npts,k", [(50000, 16), (10000, 8), (777, 3), (64, 1), (65, 32)])
+def test_sort_layout_on_shuffled_clouds_matches_oracle(npts, k):
+    """AMPC_LAYOUT_SORT: tiles over the Morton-bucketed copy; indices are still those of the
+    caller's record order, indices and dist2 bit-exact against brute force."""
+    B, Q = 5, 20
+    h = A.Handle(N=Q, K=min(k, 32), max_batch=B, max_points=npts)
+    h.cloud_set_layout(A.capi.LAYOUT_SORT)
+    clouds = [_shuffled(S.forest_cloud(300 + s, npts)[0], s) for s in range(B)]
+    clouds[1] = clouds[1][: max(1, npts - 37)]          # ragged batch
+    h.cloud_set_batch(_pad_batch(clouds, npts), counts=np.array([len(c) for c in clouds], dtype=np.int32))
+    queries = np.stack([S.states(300 + s, Q)[1][:, :3] for s in range(B)])
+    _check(h, clouds, queries, k)
+    # the caller's cloud is untouched by the bucketing
+    assert (h.cloud_get(2)[:, :3] == clouds[2][:, :3]).all()
+    h.close()
+
+
+def _pad_batch(clouds, npts):
+    out = np.zeros((len(clouds), npts, 4), dtype=np.float32)
+    for s, c in enumerate(clouds):
+        out[s, : len(c)] = c
+    return out
+
+
+def test_sort_layout_edge_cases():
+    """Empty cloud, n < k, n == k, NaN x records (dropped before the bucketing, indices refer to
+    the filtered cloud), NaN / inf in y or z, all points identical (degenerate box), and a switch
+    of the same slot back to the unorganised layout."""
+    Q, k = 6, 4
+    h = A.Handle(N=Q, K=k, max_batch=8, max_points=5000)
+    h.cloud_set_layout(A.capi.LAYOUT_SORT)
+    rng = np.random.default_rng(5)
+    q = rng.uniform(-1, 1, (1, Q, 3))
+    h.cloud_set(0, np.zeros((0, 4), dtype=np.float32))
+    idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([0], dtype=np.int32))
+    assert (cnt == 0).all() and (idx == -1).all() and np.isinf(d2).all() and (pts == 1e4).all()
+    for s, n in ((1, 3), (2, 4), (3, 5)):
+        c = S.random_cloud(20 + s, n, lo=(-1, -1, -1), hi=(1, 1, 1))
+        h.cloud_set(s, c)
+        idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([s], dtype=np.int32))
+        ri, rd, rc = O.knn_bruteforce(c, q[0], k)
+        assert (cnt[0] == rc).all() and (idx[0] == ri).all() and (d2[0] == rd).all()
+    c = S.random_cloud(31, 4321, lo=(-1, -1, -1), hi=(1, 1, 1))
+    c[::5, 0] = np.nan
+    c[7, 1] = np.nan
+    c[9, 2] = np.inf
+    c[11, 1] = -np.inf
+    h.cloud_set(4, c)
+    cf = O.filter_nan(c)
+    assert h.cloud_count(4) == len(cf)
+    idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([4], dtype=np.int32))
+    ri, rd, rc = O.knn_bruteforce(cf, q[0], k)
+    assert (idx[0] == ri).all() and (d2[0] == rd).all()
+    same = np.ones((300, 4), dtype=np.float32)
+    h.cloud_set(5, same)
+    idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([5], dtype=np.int32))
+    assert (idx[0] == np.arange(k)).all()       # exact ties in (dist2, index) order
+    # same slot, now unorganised: the layout is per scene and per build
+    h.cloud_set_layout(0)
+    c2 = S.random_cloud(33, 2000, lo=(-1, -1, -1), hi=(1, 1, 1))
+    h.cloud_set(4, c2)
+    idx, d2, pts, cnt = h.knn(q, k, scene_of=np.array([4], dtype=np.int32))
+    ri, rd, rc = O.knn_bruteforce(c2, q[0], k)
+    assert (idx[0] == ri).all() and (d2[0] == rd).all()
+    # scene 5 keeps its bucketed index while scene 4 is unorganised: mixed batch
+    qq = np.concatenate([q, q])
+    idx, d2, pts, cnt = h.knn(qq, k, scene_of=np.array([4, 5], dtype=np.int32))
+    assert (idx[0] == ri).all() and (idx[1] == np.arange(k)).all()
+    h.close()
+
+
+def test_sort_layout_large_cloud_and_segments():
+    """1M shuffled points, B = 1 (multi-segment path over the bucketed copy), uniform random
+    cloud = the worst case for the flat index."""
+    npts, Q, k = 1000000, 20, 16
+    h = A.Handle(N=Q, K=k, max_batch=1, max_points=npts)
+    h.cloud_set_layout(A.capi.LAYOUT_SORT)
+    c = S.random_cloud(4, npts, lo=(0, -20, 0), hi=(40, 20, 10))
+    h.cloud_set(0, c)
+    q = np.random.default_rng(2).uniform([0, -5, 0.5], [30, 5, 3], (1, Q, 3))
+    idx, d2, _, cnt = h.knn(q, k)
+    ri, rd, rc = O.knn_bruteforce(c, q[0], k)
+    assert (idx[0] == ri).all() and (d2[0] == rd).all()
+    h.close()
+
+
+def test_sort_layout_round_equals_unorganised_round():
+    """The control round on shuffled clouds: same neighbours, hence the same prefixes and
+    bit-identical trajectories, whatever the layout."""
+    N, K, B, npts = 20, 16, 8, 20000
+    clouds = [_shuffled(S.forest_cloud(500 + s, npts)[0], 50 + s) for s in range(B)]
+    x0, ref, _ = S.states_batch(list(range(500, 500 + B)), N, A.defaults.BENCH_DT)
+    W0 = np.stack([S.warm_start("ref", x0[b], ref[b], N) for b in range(B)])
+    res = []
+    for lay in (0, A.capi.LAYOUT_SORT):
+        h = A.Handle(N=N, K=K, max_batch=B, max_points=npts)
+        h.cloud_set_layout(lay)
+        h.cloud_set_batch(np.stack(clouds))
+        W, info, replan = h.round(x0, ref, W0)
+        res.append((W, info["cost"].copy(), replan.copy()))
+        h.close()
+    assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all() and (res[0][2] == res[1][2]).all()

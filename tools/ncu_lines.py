@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an `ncu --page source --csv` SASS dump per CUDA source line.
 
-usage: ncu_lines.py <prof.ncu-rep> <libampc.so> <kernel-substring> [top]
+usage: [DIS_KERN=<mangled substring>] ncu_lines.py <prof.ncu-rep> <libampc.so> <kernel-substring> [top]
 Joins ncu's per-SASS-instruction counters with `nvdisasm --print-line-info` of the same
 kernel (instruction order is identical) and prints executed instructions and stall
 samples per source line."""
@@ -33,7 +33,7 @@ cur_fn, cur_line, active = None, None, False
 for l in dis.splitlines():
     m = re.match(r"\s*\.text\.(\S+):", l)
     if m:
-        active = kern in m.group(1)
+        active = os.environ.get("DIS_KERN", kern) in m.group(1)
         continue
     if not active:
         continue
