@@ -100,32 +100,53 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------ GPU arm ----
 class ClockSampler:
+    """nvidia-smi polled every 50 ms by a reader thread that stamps each sample on arrival; the
+    samples that arrived inside [mark_begin(), mark_end()] are reported.  nvidia-smi needs about
+    a second to deliver its first sample, so it is started before the warm-up and the window
+    covers the loaded warm-up steps plus the timed region (the GPU is busy throughout)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, dev):
-        self.dev, self.p = dev, None
+        self.dev, self.p, self.rows, self.t0, self.t1, self.thread = dev, None, [], None, None, None
 
     def start(self):
+        import threading
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
+                                       "-lms", "50", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
         except OSError:
             self.p = None
+            return
+
+        def reader():
+            for line in self.p.stdout:
+                self.rows.append((time.perf_counter(), line))
+        self.thread = threading.Thread(target=reader, daemon=True)
+        self.thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
         try:
-            out = self.p.communicate(timeout=5)[0]
+            self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-            out = ""
+        if self.thread:
+            self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in out.strip().splitlines():
+        for ts, line in list(self.rows):
+            if self.t0 is not None and (ts < self.t0 or ts > (self.t1 or ts) + 0.05):
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -137,7 +158,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "loaded warm-up steps + single-stream pass + timed region"}
 
 
 def run_ours(args):
@@ -230,7 +252,17 @@ def run_ours(args):
         barrier()
         return start.elapsed_time(end), [a.elapsed_time(b) for a, b in sev]
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
+        for ln in lanes:
+            step(ln)
+    barrier()
+    # keep the GPU loaded (untimed; the same count on every rank) until the clock sampler has
+    # something to report, then go straight into the measured passes
+    sampler.mark_begin()
+    for _ in range(args.load_rounds):
         for ln in lanes:
             step(ln)
     barrier()
@@ -241,10 +273,6 @@ def run_ours(args):
     single_ms, single_step_ms = timed(lanes[:1], n_single)
     prof1 = lanes[0]["h"].profile_get()
     lanes[0]["h"].profile_enable(False)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     for ln in lanes:
         ln["h"].profile_enable(True)
     l0 = sum(ln["h"].launch_count() for ln in lanes)
@@ -263,6 +291,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     info = lanes[0]["info"]
     replan = lanes[0]["replan"]
@@ -656,7 +685,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unorganised", action="store_true", help="do not pass the image row pitch to the index")
     ap.add_argument("--mode", default="solves", choices=["solves", "knn_sweep", "cpu_c0"])
-    ap.add_argument("--streams", type=int, default=4, help="independent batches in flight per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="independent batches in flight per GPU")
+    ap.add_argument("--load-rounds", type=int, default=100,
+                    help="untimed rounds over all lanes before the measured passes (clock sampling window)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
