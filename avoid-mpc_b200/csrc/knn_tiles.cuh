@@ -266,6 +266,7 @@ cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes
         }
     };
     bool nan_seen = false;
+    const int full_rows = row_w > 0 ? n / row_w : 0, rem_cols = row_w > 0 ? n - full_rows * row_w : 0;
     if (tid == 0)
         issue(b_begin, 0);
     for (int b = b_begin; b < b_end; ++b) {
@@ -275,33 +276,74 @@ cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes
         mbar_wait(&bar[cur], (it >> 1) & 1);
         const float4 *sb = buf[cur];
         const int by = b / segs_x, bxs = b - by * segs_x;
+        // Four tiles per warp pass, one per quarter-warp: lane (q, l) walks the 8 records of
+        // column l of tile q (organised: the 8 image rows of the patch; unorganised: records
+        // l, l + 8, ..), folding min / max / valid-count in registers; three xor-shuffles
+        // finish the tile inside its 8 lanes.  Every shared-memory read is 512 contiguous
+        // bytes per warp (organised) or four 128-byte runs (unorganised).
+        const int qd = lane >> 3, l8 = lane & 7;
+        int tiles_here, tile0, pitch = 0, col0 = 0, c0 = 0;
         if (row_w > 0) {
-            const int c0 = bxs * KI_COLS, cols = min(KI_COLS, row_w - c0);
-            const int tiles_here = (cols + 7) / 8;
-            const int r0 = lane >> 3, cc = lane & 7;
-            const int pitch = row_w <= KI_COLS ? row_w : KI_COLS; // records between rows in shared memory
-            for (int j = warp; j < tiles_here; j += NW) {
-                const int col = 8 * j + cc;
-                const int64_t i0 = (int64_t)(8 * by + r0) * row_w + c0 + col, i1 = i0 + 4 * (int64_t)row_w;
-                const bool v0 = col < cols && i0 < n, v1 = col < cols && i1 < n;
-                float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
-                if (v0) p0 = sb[r0 * pitch + col];
-                if (v1) p1 = sb[(r0 + 4) * pitch + col];
-                nan_seen |= (v0 && p0.x != p0.x) || (v1 && p1.x != p1.x);
-                tile_box_store(bx, (int64_t)by * g.tiles_x + c0 / 8 + j, p0, p1, v0, v1, lane);
-            }
+            c0 = bxs * KI_COLS;
+            col0 = min(KI_COLS, row_w - c0);            // valid columns of this band
+            tiles_here = (col0 + 7) / 8;
+            tile0 = by * g.tiles_x + c0 / 8;
+            pitch = row_w <= KI_COLS ? row_w : KI_COLS; // records between rows in shared memory
         } else {
-            const int64_t start = (int64_t)b * 8 * KI_COLS;
-            const int cnt = (int)min((int64_t)8 * KI_COLS, (int64_t)n - start);
-            const int tiles_here = (cnt + KT_TILE - 1) / KT_TILE;
-            for (int j = warp; j < tiles_here; j += NW) {
-                const int s0 = j * KT_TILE + lane, s1 = s0 + 32;
-                const bool v0 = s0 < cnt, v1 = s1 < cnt;
-                float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
-                if (v0) p0 = sb[s0];
-                if (v1) p1 = sb[s1];
-                nan_seen |= (v0 && p0.x != p0.x) || (v1 && p1.x != p1.x);
-                tile_box_store(bx, start / KT_TILE + j, p0, p1, v0, v1, lane);
+            const int start = b * 8 * KI_COLS;
+            col0 = min(8 * KI_COLS, n - start);         // records in this band
+            tiles_here = (col0 + KT_TILE - 1) / KT_TILE;
+            tile0 = start / KT_TILE;
+        }
+        for (int j4 = 4 * warp; j4 < tiles_here; j4 += 4 * NW) {
+            const int t = j4 + qd;
+            float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+            int cnt = 0;
+            if (row_w > 0) {
+                // rows of this column that exist: image rows < full_rows are complete, row
+                // full_rows holds the first rem_cols columns
+                const int col = 8 * t + l8;
+                int nv = full_rows - 8 * by + (c0 + col < rem_cols ? 1 : 0);
+                nv = col < col0 ? min(max(nv, 0), 8) : 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < nv) {
+                        const float4 p = sb[i * pitch + col];
+                        nan_seen |= p.x != p.x;
+                        lx = fminf(lx, p.x), ly = fminf(ly, p.y), lz = fminf(lz, p.z); // NaN drops out
+                        hx = fmaxf(hx, p.x), hy = fmaxf(hy, p.y), hz = fmaxf(hz, p.z);
+                        const float sum = p.x + p.y + p.z; // NaN iff some coordinate is NaN (or inf - inf:
+                        cnt += sum == sum;                 // an under-count, which is safe)
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int sidx = KT_TILE * t + 8 * i + l8;
+                    if (sidx < col0) {
+                        const float4 p = sb[sidx];
+                        nan_seen |= p.x != p.x;
+                        lx = fminf(lx, p.x), ly = fminf(ly, p.y), lz = fminf(lz, p.z);
+                        hx = fmaxf(hx, p.x), hy = fmaxf(hy, p.y), hz = fmaxf(hz, p.z);
+                        const float sum = p.x + p.y + p.z;
+                        cnt += sum == sum;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                lx = fminf(lx, __shfl_xor_sync(AMPC_FULL_MASK, lx, o));
+                ly = fminf(ly, __shfl_xor_sync(AMPC_FULL_MASK, ly, o));
+                lz = fminf(lz, __shfl_xor_sync(AMPC_FULL_MASK, lz, o));
+                hx = fmaxf(hx, __shfl_xor_sync(AMPC_FULL_MASK, hx, o));
+                hy = fmaxf(hy, __shfl_xor_sync(AMPC_FULL_MASK, hy, o));
+                hz = fmaxf(hz, __shfl_xor_sync(AMPC_FULL_MASK, hz, o));
+                cnt += __shfl_xor_sync(AMPC_FULL_MASK, cnt, o);
+            }
+            if (l8 == 0 && t < tiles_here) {
+                float4 *dst = bx + 2 * (int64_t)(tile0 + t);
+                dst[0] = make_float4(lx, ly, lz, hx);
+                dst[1] = make_float4(hy, hz, __int_as_float(cnt), 0.f);
             }
         }
         __syncthreads(); // everyone is done with buf[cur]: it may be refilled
