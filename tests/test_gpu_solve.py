@@ -73,3 +73,32 @@ def test_status_reports_iteration_cap():
     oW, ost, oit, _ = oracle_solve_batch(N, K, 0.05, inst["params"], W0, max_iter=2)
     assert np.abs(W - oW).max() < 1e-8  # same two iterates
     h.close()
+
+
+def test_solve_matches_full_space_interior_point_golden():
+    """The CUDA solve against optima computed by an independent interior-point solver (scipy
+    trust-constr) on the reference's full-space formulation (tests/golden/make_solve_golden.py):
+    same point wherever that solver converged, l_inf < 1e-4 on states and controls."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "solve_golden.npz"))
+    groups = {}
+    for i in range(int(G["n"])):
+        sid, N, K, npts, ref_warm = (int(v) for v in G[f"i{i}_meta"])
+        groups.setdefault((N, K), []).append(i)
+    checked = 0
+    for (N, K), ids in groups.items():
+        dt = 0.05 if N == 20 else 1.0 / N
+        n_prefix = 20 + 10 * N + 3 * K * N
+        P = np.stack([G[f"i{i}_p"][:n_prefix] for i in ids])
+        W0 = np.stack([G[f"i{i}_w0"] for i in ids])
+        h = A.Handle(N=N, K=K, dt=dt, max_batch=len(ids), max_points=16)
+        W, info = h.solve(P, W0)
+        h.close()
+        assert (info["status"] == A.capi.SOLVE_CONVERGED).all()
+        for j, i in enumerate(ids):
+            if not bool(G[f"i{i}_conv"]):
+                continue
+            checked += 1
+            assert np.abs(W[j] - G[f"i{i}_w"]).max() < TRAJ_TOL, (N, K, i)
+            assert abs(info["cost"][j] - float(G[f"i{i}_cost"])) <= 1e-7 * abs(float(G[f"i{i}_cost"]))
+    assert checked >= 49
