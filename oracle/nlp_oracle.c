@@ -11,8 +11,11 @@
  * that script (tests/test_oracle_nlp.py).  The *solver* in the reference is
  * CasADi 3.6.4 -> IPOPT -> MUMPS (README.md:41-43), none of which exist in this
  * image, and the reference ships no golden vector for it; so the solve is
- * checked at convergence against scipy.optimize trust-constr on the same NLP,
- * not against IPOPT.
+ * checked at convergence against an independent interior-point solver of the
+ * same class (scipy.optimize trust-constr on the reference's full-space
+ * formulation: w = [X, U], g(w) = 0, bounds on U, exact Hessian; 52 golden
+ * optima in tests/golden/solve_golden.npz, minted by
+ * tests/golden/make_solve_golden.py), not against IPOPT.
  *
  * Reference (paths under roswrapper/ros/src/avoid_mpc/):
  *   tools/mpc_obstacle_casadi.py:36-48    dimensions (s_dim 10, u_dim 4, weights 25)
