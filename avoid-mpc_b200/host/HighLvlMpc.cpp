@@ -45,6 +45,14 @@ void ObstacleAvoidanceMPC::SetDroneAccelLimits(const double aMinZ, const double 
     mParamsDirty = true;
 }
 
+void ObstacleAvoidanceMPC::SetSolverOptions(double tol, int maxIter) {
+    if (!(tol > 0) || maxIter < 0)
+        throw std::runtime_error("ObstacleAvoidanceMPC::SetSolverOptions: need tol > 0 and maxIter >= 0");
+    mTol = tol;
+    mMaxIter = maxIter;
+    mParamsDirty = true;
+}
+
 void ObstacleAvoidanceMPC::EnsureHandle(int K) {
     if (mHandle && K == mK)
         return;
@@ -73,6 +81,12 @@ void ObstacleAvoidanceMPC::PushParams() {
         ampc_set_gains(h, mGains.data()) || ampc_set_radius(h, mDroneRadius) ||
         ampc_set_accel_limits(h, mLimits[0], mLimits[1], mLimits[2], mLimits[3]))
         die(h, "setting parameters");
+    ampc_solver_opts o;
+    ampc_default_solver_opts(&o);
+    o.tol = mTol;
+    o.max_iter = mMaxIter;
+    if (ampc_set_solver_opts(h, &o))
+        die(h, "ampc_set_solver_opts");
     mParamsDirty = false;
 }
 

@@ -31,7 +31,11 @@ public:
     void SetDroneAccelLimits(const double aMinZ, const double aMaxZ, const double aMaxXy,
                              const double aMaxYawDot);
 
-    // additions (the reference ignores IPOPT's status, HighLvlMpc.cpp:116-122)
+    // additions.  The reference hands IPOPT tol = 1e-4 and max_iter = 10 (HighLvlMpc.cpp:17-23) and
+    // uses whatever iterate it stops at; this class solves to convergence by default (KKT <= 1e-8,
+    // at most 100 iterations).  SetSolverOptions restores a cap for hard real-time use.
+    void SetSolverOptions(double tol, int maxIter);
+    // (the reference ignores IPOPT's status, HighLvlMpc.cpp:116-122)
     int LastStatus() const { return mLastStatus; }   // AMPC_SOLVE_*
     int LastIterations() const { return mLastIters; }
     double LastCost() const { return mLastCost; }
@@ -45,6 +49,8 @@ private:
     std::vector<double> mTau, mGains, mWeights, mNlpW0;
     double mLimits[4] = {1., 20., 10., 10.}; // aMinZ, aMaxZ, aMaxXy, aMaxYawDot (HighLvlMpc.cpp:13-16)
     bool mParamsDirty = true;
+    double mTol = 1e-8;
+    int mMaxIter = 100;
     int mLastStatus = -1, mLastIters = 0;
     double mLastCost = 0;
     std::shared_ptr<ampc_handle> mHandle; // shared by copies (the reference copy-assigns the
