@@ -60,3 +60,18 @@ def test_tie_detection():
     c[:, 0] = [1, -1, 2, -2, 3, -3, 4, -4]
     assert not O.is_tie_free(c, np.array([[0.0, 1.0, 1.0]]), 3)
     assert O.is_tie_free(c, np.array([[0.1, 1.0, 1.0]]), 3)
+
+
+def test_restatement_matches_sklearn_kdtree():
+    """The reference's own Python harness queries obstacles with sklearn.neighbors.KDTree
+    (tools/mpc_obstacle_casadi.py:10,457,482): same neighbours, same order, on a tie-free cloud
+    (sklearn's distances are float64 from float64 copies of the float32 points: equal to 1e-12)."""
+    from sklearn.neighbors import KDTree
+    c = S.forest_cloud(77, 10000)[0]
+    q = S.states(77, 20)[1][:, :3]
+    k = 16
+    assert O.is_tie_free(c, q, k)
+    idx, d2, cnt = O.knn_bruteforce(c, q, k)
+    dist, ind = KDTree(c[:, :3].astype(np.float64), leaf_size=10).query(q, k=k)
+    assert (cnt == k).all() and (ind == idx).all()
+    assert np.abs(dist ** 2 - d2).max() <= 1e-12 * d2.max()
