@@ -81,6 +81,14 @@ struct ampc_handle {
     DevBuf tk_active, tk_q0, tk_d1, tk_c1, tk_ep, tk_ec, tk_ed, tk_safe, tk_rounds; // tick loop
     int64_t launches = 0;
     std::string err;
+    // quad solve kernel: workspace of the resident warps, refill counter, tuning knobs
+    DevBuf quad_ws, quad_counter;
+    int n_sm = 148;
+    int smem_per_sm = 228 * 1024;
+    int quad_warps_per_sm = 8; // AMPC_QUAD_WARPS_PER_SM (255 registers per thread allow 8)
+    int quad_per_warp = 0;     // AMPC_QUADS_PER_WARP (1, 2, 4, 8): 0 = by batch size
+    int solve_kernel = 0;      // AMPC_SOLVE_KERNEL: 0 auto (by batch size), 1 warp, 2 quad
+    int quad_min_batch = 8192; // AMPC_QUAD_MIN_BATCH: smallest batch the quad kernel takes in auto mode
     int solve_smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     int solve_warps = 2;
     int solve_smem_pad = 0; // AMPC_SOLVE_SMEM_PAD: extra dynamic shared memory per CTA (occupancy experiments)
@@ -172,6 +180,18 @@ void refresh_consts(ampc_handle *h) {
     c.N = h->cfg.N;
     c.K = h->cfg.K;
     c.n_prefix = h->n_prefix;
+    for (int i = 0; i < 4; ++i) {
+        Chain &f = c.ch[i];
+        if (i < 3) {
+            f.d1 = c.Phi[i * 10 + i], f.c1 = c.Phi[i * 10 + 4 + i], f.c2 = c.Phi[i * 10 + 7 + i];
+            f.d2 = c.Phi[(4 + i) * 10 + 4 + i], f.c3 = c.Phi[(4 + i) * 10 + 7 + i];
+            f.c4 = c.Phi[(7 + i) * 10 + 7 + i];
+            f.g1 = c.Gam[i * 4 + i], f.g2 = c.Gam[(4 + i) * 4 + i], f.g3 = c.Gam[(7 + i) * 4 + i];
+        } else {
+            f.d1 = c.Phi[33], f.c1 = f.c2 = f.d2 = f.c3 = f.c4 = 0.0;
+            f.g1 = c.Gam[15], f.g2 = f.g3 = 0.0;
+        }
+    }
     h->consts_dirty = false;
 }
 
@@ -484,6 +504,7 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
 template <int W>
 int launch_solve_w(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
                    cudaStream_t st, const int32_t *active) {
+    using namespace ampc::v1;
     const size_t smem = solve_smem_bytes(h->cfg.N, W) + (size_t)h->solve_smem_pad;
     if (smem > 227 * 1024)
         return fail(h, AMPC_ERR_UNSUPPORTED, "horizon too long for the per-warp shared-memory layout");
@@ -498,14 +519,87 @@ int launch_solve_w(ampc_handle *h, int B, const double *prefix_dev, double *w_de
     return AMPC_OK;
 }
 
+// Quad kernel (ipm_quad.cuh): persistent one-warp CTAs with Q = 1, 2, 4 or 8 instances in flight
+// per warp.  Shared memory per warp grows with Q (and N), registers allow 8 warps per SM.
+int quad_warps_per_sm(const ampc_handle *h, int Q) {
+    const size_t smem = quad_smem_bytes(h->cfg.N, Q) + 1024; // + the per-CTA reservation
+    int w = (int)((size_t)h->smem_per_sm / smem);
+    if (w > h->quad_warps_per_sm) w = h->quad_warps_per_sm;
+    return w;
+}
+int launch_solve_quad(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
+                      cudaStream_t st, const int32_t *active) {
+    // 8 instances per warp amortise the sweep best (measured: B = 32768 in 29.3 ms with 8, 35.7 ms
+    // with 4); fewer only when the shared-memory state of 8 does not fit (long horizons)
+    int qs = 3;
+    if (h->quad_per_warp > 0)
+        for (qs = 0; (1 << qs) < h->quad_per_warp; ++qs) {}
+    while (qs > 0 && quad_warps_per_sm(h, 1 << qs) < 1) --qs;
+    const int Q = 1 << qs;
+    const int per_sm = quad_warps_per_sm(h, Q);
+    if (per_sm < 1)
+        return fail(h, AMPC_ERR_UNSUPPORTED, "horizon too long for the shared-memory state of one instance");
+    const int cap = h->n_sm * per_sm; // resident warps
+    int warps = (B + Q - 1) / Q;
+    if (warps > cap) warps = cap;
+    const size_t smem = quad_smem_bytes(h->cfg.N, Q);
+    {
+        // the attribute belongs to the function, not to the handle: only ever raise it
+        static std::mutex mtx;
+        static int set_to[64][4] = {{0}};
+        std::lock_guard<std::mutex> g(mtx);
+        const int dev = h->cfg.device & 63;
+        if ((int)smem > set_to[dev][qs]) {
+            const void *fn = qs == 0 ? (const void *)ipm_quad_kernel<0>
+                           : qs == 1 ? (const void *)ipm_quad_kernel<1>
+                           : qs == 2 ? (const void *)ipm_quad_kernel<2> : (const void *)ipm_quad_kernel<3>;
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            set_to[dev][qs] = (int)smem;
+        }
+    }
+    const size_t need = (size_t)warps * quad_ws_bytes_per_warp(h->cfg.N, Q);
+    if (need > h->quad_ws.bytes) {
+        CK(cudaStreamSynchronize(st));
+        size_t full = 0; // enough for any packing
+        for (int t = 0; t <= 3; ++t) {
+            const size_t v = (size_t)h->n_sm * (size_t)(quad_warps_per_sm(h, 1 << t) > 0 ? quad_warps_per_sm(h, 1 << t) : 0) *
+                             quad_ws_bytes_per_warp(h->cfg.N, 1 << t);
+            if (v > full) full = v;
+        }
+        CK(h->quad_ws.reserve(full > need ? full : need));
+    }
+    CK(h->quad_counter.reserve(256));
+    CK(cudaMemsetAsync(h->quad_counter.p, 0, 4, st));
+    double *wsp = h->quad_ws.as<double>();
+    int32_t *cnt = h->quad_counter.as<int32_t>();
+    switch (qs) {
+    case 0: ipm_quad_kernel<0><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
+    case 1: ipm_quad_kernel<1><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
+    case 2: ipm_quad_kernel<2><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
+    default: ipm_quad_kernel<3><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return AMPC_OK;
+}
+
 int launch_solve(ampc_handle *h, int B, const double *prefix_dev, double *w_dev, SolveOut *info_dev,
                  cudaStream_t st, const int32_t *active = nullptr) {
     refresh_consts(h);
+    // Two kernels for one algorithm.  Small batches: one warp per instance (lowest latency, the
+    // machine is not full anyway).  Large batches: four lanes per instance, eight instances per
+    // persistent warp with refill from a queue (fewest instructions per solve).  Measured on B200
+    // (solve stage, ms, warp / quad): B = 4096: 9.0 / 11.9, 8192: 13.8 / 13.6, 16384: 23.7 / 17.6,
+    // 32768: 43.5 / 29.3.
+    const bool warp_fits = ampc::v1::solve_smem_bytes(h->cfg.N, 1) <= 227 * 1024;
+    const bool use_quad = h->solve_kernel == 2 || !warp_fits || (h->solve_kernel == 0 && B >= h->quad_min_batch);
+    if (use_quad)
+        return launch_solve_quad(h, B, prefix_dev, w_dev, info_dev, st, active);
     // warps (= instances) per CTA (AMPC_SOLVE_WARPS; measured best at C1: 2): the warps of a CTA start
     // every iteration together (shared instruction cache); horizons too long for the per-warp
     // shared memory of W warps fall back to fewer
     int W = h->solve_warps;
-    while (W > 1 && solve_smem_bytes(h->cfg.N, W) > 227 * 1024)
+    while (W > 1 && ampc::v1::solve_smem_bytes(h->cfg.N, W) > 227 * 1024)
         W >>= 1;
     switch (W) {
     case 8: return launch_solve_w<8>(h, B, prefix_dev, w_dev, info_dev, st, active);
@@ -584,6 +678,27 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
         const int v = std::atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) h->solve_warps = v;
     }
+    if (const char *e = std::getenv("AMPC_SOLVE_KERNEL"))
+        h->solve_kernel = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "quad") == 0 ? 2 : 0);
+    if (const char *e = std::getenv("AMPC_QUAD_MIN_BATCH")) {
+        const int v = std::atoi(e);
+        if (v >= 1) h->quad_min_batch = v;
+    }
+    if (const char *e = std::getenv("AMPC_QUADS_PER_WARP")) {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) h->quad_per_warp = v;
+    }
+    if (const char *e = std::getenv("AMPC_QUAD_WARPS_PER_SM")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 16) h->quad_warps_per_sm = v;
+    }
+    {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, cfg->device) == cudaSuccess && v > 0)
+            h->n_sm = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, cfg->device) == cudaSuccess && v > 0)
+            h->smem_per_sm = v;
+    }
     if (const char *e = std::getenv("AMPC_SOLVE_SMEM_PAD")) {
         const int v = std::atoi(e);
         if (v > 0 && v < 200 * 1024) h->solve_smem_pad = v & ~15;
@@ -653,7 +768,7 @@ void ampc_destroy(ampc_handle *h) {
                      &h->depth_scratch, &h->depth_flag, &h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
-                     &h->ws_i, &h->ws_counter, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
+                     &h->ws_i, &h->ws_counter, &h->quad_ws, &h->quad_counter, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
                      &h->tk_c1, &h->tk_ep, &h->tk_ec, &h->tk_ed, &h->tk_safe, &h->tk_rounds};
     for (DevBuf *b : all)
         b->release();

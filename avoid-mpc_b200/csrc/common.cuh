@@ -29,8 +29,16 @@ __device__ __forceinline__ double warp_min(double v) {
     return v;
 }
 
-// Handle-level constants of the NLP, passed to the solve kernel by value and
-// staged into shared memory once per CTA.
+// The affine dynamics (tools/mpc_obstacle_casadi.py:106-122) decouple into four chains: axis
+// i < 3 with components (p_i, v_i, a_i) = state indices (i, 4+i, 7+i) driven by control i, and
+// yaw (component 0 = state 3, control 3; components 1, 2 are padding that stays exactly zero).
+// Chain i advances by the upper-triangular 3x3 matrix F_i and the 3-vector G_i:
+struct Chain {
+    double d1, c1, c2, d2, c3, c4; // F = [[d1,c1,c2],[0,d2,c3],[0,0,c4]]
+    double g1, g2, g3;             // G
+};
+
+// Handle-level constants of the NLP, passed to the solve kernels by value.
 struct SolveConsts {
     double Phi[100], Gam[40], gam[10]; // X+ = Phi X + Gam U + gam (RK4x4 of the affine ODE)
     double wgt[25];                    // [Q_goal(10) | Q_pen(10) | Q_u(4) | lambda]
@@ -38,6 +46,7 @@ struct SolveConsts {
     double lb[4], ub[4];
     double tol, mu_init, bound_push, bound_frac, eps_min, eps_scale, kappa_eps;
     int32_t max_iter, N, K, n_prefix;
+    Chain ch[4];                       // the same Phi / Gam, chain by chain
 };
 
 } // namespace ampc

@@ -28,10 +28,10 @@
 // iterate, the step, gradients, compact (p,v) Hessian blocks and the feedback gains.
 #pragma once
 #include "common.cuh"
+#include "ipm_quad.cuh" // SolveOut
 
 namespace ampc {
-
-#define AMPC_GZ 9.81 // tools/mpc_obstacle_casadi.py:39
+namespace v1 { // round-1 kernel, kept for A/B measurements (AMPC_SOLVE_KERNEL=warp)
 
 // per-warp shared-memory layout, in doubles
 struct WarpLayout {
@@ -67,10 +67,6 @@ __host__ __device__ inline size_t solve_smem_bytes(int N, int warps) {
 // components (p_i, v_i, a_i) = state indices (i, 4+i, 7+i) driven by control i, and yaw
 // (component 0 = state 3; components 1,2 are padding that stays exactly zero).  Chain i
 // advances by the upper-triangular 3x3 matrix F_i and the 3-vector G_i below.
-struct Chain {
-    double d1, c1, c2, d2, c3, c4; // F = [[d1,c1,c2],[0,d2,c3],[0,0,c4]]
-    double g1, g2, g3;             // G
-};
 __device__ __forceinline__ Chain load_chain(const double *Phi, const double *Gam, int i) {
     Chain c;
     if (i < 3) {
@@ -416,7 +412,7 @@ __device__ __noinline__ double adjoint_dual_inf(const WarpCtx &w) {
         const double qk1 = m_ax * s[L.q + 10 * k + q1];
         const double qk2 = m_ax * s[L.q + 10 * k + q2];
         double fl[3];
-        chain_FT(fi, lv, fl);
+        v1::chain_FT(fi, lv, fl);
         lv[0] = qk0 + fl[0], lv[1] = qk1 + fl[1], lv[2] = qk2 + fl[2];
     }
     return warp_max(e_dual);
@@ -477,7 +473,7 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta) {
         for (int a = 0; a < 3; ++a)
             t[a] = P[3 * a] * fj.g1 + P[3 * a + 1] * fj.g2 + P[3 * a + 2] * fj.g3;
         const double Sij = fi.g1 * t[0] + fi.g2 * t[1] + fi.g3 * t[2] + m_diag * (rdk + delta);
-        chain_FT(fi, t, bm);
+        v1::chain_FT(fi, t, bm);
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             M[3 * a] = fj.d1 * P[3 * a];
@@ -564,7 +560,7 @@ __device__ __noinline__ bool riccati_backward(const WarpCtx &w, double delta) {
                                yy * bm[a] * bm[b];
         P[0] += Qb0, P[1] += Qb1, P[3] += Qb3, P[4] += Qb4, P[8] += q22c;
         double fp[3];
-        chain_FT(fi, pv, fp);
+        v1::chain_FT(fi, pv, fp);
         const double kq[3] = {qk0, qk1, qk2};
         const double ky = yaw ? kff3 : 0.0;
 #pragma unroll
@@ -646,11 +642,6 @@ __device__ __noinline__ void rollout_delta(const WarpCtx &w) {
     }
     __syncwarp();
 }
-
-struct SolveOut {
-    double cost, kkt_dual, kkt_compl, mu;
-    int32_t iters, status, n_reg, n_backtrack;
-};
 
 template <bool SYNC>
 __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out) {
@@ -918,4 +909,5 @@ ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double
     solve_instance<(WARPS > 1)>(ctx, w_inout + (size_t)b * (10 + 14 * sc->N), info + b);
 }
 
+} // namespace v1
 } // namespace ampc

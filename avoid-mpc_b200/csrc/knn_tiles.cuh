@@ -83,9 +83,18 @@ struct TileGeom {
         return i < n ? i : -1;
     }
 };
-// upper bound of TileGeom(n, w).n_tiles over n <= max_points, any w >= 8
+// tile slots per scene: enough for the linear layout and for every organised cloud that spans
+// at least 8 rows; a wider row hint (n_tiles grows to ceil(w/8) for a 1-row cloud) falls back
+// to the linear layout through tile_layout() below, in every kernel alike
 __host__ __device__ inline int64_t tile_capacity(int64_t max_points) {
     return 2 * ((max_points + KT_TILE - 1) / KT_TILE) + 64;
+}
+// the layout a scene of n points is actually indexed with: its hint, unless the 8x8-patch
+// tiling of that hint would need more tile slots than the scene has
+__host__ __device__ inline int tile_layout(int n, int hint, int64_t slot_tiles) {
+    if (hint > 0 && TileGeom(n, hint).n_tiles > slot_tiles)
+        return 0;
+    return hint;
 }
 
 struct KnnParams {
@@ -213,10 +222,10 @@ cloud_index_kernel(const float4 *__restrict__ clouds, float4 *__restrict__ boxes
     __shared__ __align__(8) unsigned long long bar[2];
     float4 *buf[2] = {reinterpret_cast<float4 *>(ki_smem), reinterpret_cast<float4 *>(ki_smem + KI_BAND_BYTES)};
     const int scene = first_scene + blockIdx.x; // scenes on x: no 65535 limit
-    const int row_w = layout[scene];
     const float4 *c = clouds + (int64_t)scene * slot_points;
     float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
     const int n = counts[scene];
+    const int row_w = tile_layout(n, layout[scene], slot_tiles);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = KI_THREADS / 32;
     const TileGeom g(n, row_w);
@@ -403,7 +412,7 @@ cloud_compact_kernel(float4 *clouds, float4 *boxes, int32_t *counts, int32_t *na
         counts[scene] = m;
         nan_flags[scene] = 0;
     }
-    const TileGeom g(m, row_w);
+    const TileGeom g(m, tile_layout(m, row_w, slot_tiles));
     for (int t = warp; t < g.n_tiles; t += NW) {
         const int i0 = g.point(t, lane, m), i1 = g.point(t, lane + 32, m);
         float4 p0 = make_float4(0, 0, 0, 0), p1 = p0;
@@ -750,7 +759,7 @@ knn_search_kernel(const KnnParams P) {
     const float4 *boxes = P.boxes + (int64_t)scene * P.slot_tiles * 2;
     const double *qp = P.queries + ((int64_t)b * P.Q + q) * 3;
     const double qx = qp[0], qy = qp[1], qz = qp[2];
-    const int lay = P.layout[scene];
+    const int lay = tile_layout(n, P.layout[scene], P.slot_tiles);
     const bool by_w = lay < 0; // tiles over the Morton-bucketed copy; indices come from its pad word
     const float4 *tsrc = by_w ? P.sorted + (int64_t)scene * P.slot_points : cloud;
     const TileGeom g(n, lay);

@@ -13,6 +13,14 @@ TRAJ_TOL = 1e-4   # north-star tolerance on state/control trajectories (l_inf)
 TIGHT_TOL = 1e-6  # what the two implementations actually agree to at convergence
 
 
+@pytest.fixture(params=["warp", "quad"], autouse=True)
+def solve_kernel(request, monkeypatch):
+    """Every test of this file runs on both solve kernels (the library picks by batch size:
+    one warp per instance below 8192 instances, four lanes per instance above)."""
+    monkeypatch.setenv("AMPC_SOLVE_KERNEL", request.param)
+    return request.param
+
+
 def test_dynamics_match_oracle():
     h = A.Handle(N=20, K=16, max_batch=1, max_points=16)
     Phi, Gam, gam = h.dynamics()
@@ -102,3 +110,43 @@ def test_solve_matches_full_space_interior_point_golden():
             assert np.abs(W[j] - G[f"i{i}_w"]).max() < TRAJ_TOL, (N, K, i)
             assert abs(info["cost"][j] - float(G[f"i{i}_cost"])) <= 1e-7 * abs(float(G[f"i{i}_cost"]))
     assert checked >= 49
+
+
+def test_quad_kernel_refill_and_packing_do_not_change_results(monkeypatch):
+    """The quad kernel's results must not depend on how instances share warps: 1, 2, 4 or 8
+    instances per warp, with and without refill from the queue (one resident warp per SM and
+    2 instances per warp -> 296 slots for 400 instances), bit for bit; and they must agree with
+    the warp-per-instance kernel to rounding."""
+    N, K, B = 20, 16, 400
+    inst = make_instances([500 + (b % 40) for b in range(B)], N, K, 10000)
+    rng = np.random.default_rng(7)
+    W0 = np.stack([S.warm_start("ref", inst["x0"][b], inst["ref"][b], N) for b in range(B)])
+    W0[:, :] += 0.0
+    for b in range(B):  # distinct problems from 40 scenes: perturb the warm-start controls
+        for k in range(N):
+            W0[b, 14 * k + 10:14 * k + 14] += rng.normal(0, 0.3, 4) * (b // 40)
+    results = {}
+    for name, env in [("warp", {"AMPC_SOLVE_KERNEL": "warp"}),
+                      ("q8", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "8"}),
+                      ("q4", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "4"}),
+                      ("q1", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "1"}),
+                      ("q2_refill", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "2",
+                                     "AMPC_QUAD_WARPS_PER_SM": "1"})]:
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        h = A.Handle(N=N, K=K, max_batch=B, max_points=16)
+        results[name] = h.solve(inst["prefix"], W0)
+        h.close()
+        monkeypatch.delenv("AMPC_QUADS_PER_WARP", raising=False)
+        monkeypatch.delenv("AMPC_QUAD_WARPS_PER_SM", raising=False)
+    W8, i8 = results["q8"]
+    for name in ("q4", "q1", "q2_refill"):
+        W, info = results[name]
+        assert (W == W8).all(), name
+        for f in ("cost", "iters", "status", "n_reg", "n_backtrack"):
+            assert (info[f] == i8[f]).all(), (name, f)
+    Ww, iw = results["warp"]
+    both = (iw["status"] == 0) & (i8["status"] == 0)
+    assert both.mean() > 0.9
+    assert (np.abs(Ww - W8).max(axis=1)[both] < TRAJ_TOL).mean() >= 0.98
+    assert np.median(np.abs(Ww - W8).max(axis=1)[both]) < TIGHT_TOL
