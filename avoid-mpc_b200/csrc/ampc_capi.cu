@@ -875,14 +875,21 @@ static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_sce
     if (maxc > 0) {
         if (stride == 16) {
             char *dst = reinterpret_cast<char *>(slots) + (int64_t)first_scene * slot_bytes;
+            // the caller's buffer is only promised to hold counts[s] records of scene s: never read
+            // past the last scene's own points
+            const int last = counts[n_scenes - 1];
             if (n_scenes == 1 || (scene_stride == slot_bytes && maxc == h->slot_points[kind])) {
-                const size_t bytes = n_scenes == 1 ? (size_t)maxc * 16 : (size_t)n_scenes * slot_bytes;
-                CK(cudaMemcpyAsync(dst, src, bytes, dir, st));
+                const size_t bytes = (size_t)(n_scenes - 1) * slot_bytes + (size_t)last * 16;
+                if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, dir, st));
             } else {
                 if (scene_stride < (int64_t)maxc * 16)
                     return fail(h, AMPC_ERR_INVALID, "scene_stride_bytes smaller than the largest cloud");
                 CK(cudaMemcpy2DAsync(dst, (size_t)slot_bytes, src, (size_t)scene_stride, (size_t)maxc * 16,
-                                     (size_t)n_scenes, dir, st));
+                                     (size_t)(n_scenes - 1), dir, st));
+                if (last)
+                    CK(cudaMemcpyAsync(dst + (int64_t)(n_scenes - 1) * slot_bytes,
+                                       static_cast<const char *>(src) + (int64_t)(n_scenes - 1) * scene_stride,
+                                       (size_t)last * 16, dir, st));
             }
         } else {
             if (n_scenes > 1 && scene_stride < (int64_t)maxc * stride)
@@ -891,7 +898,8 @@ static int cloud_set_common(ampc_handle *h, int kind, int first_scene, int n_sce
             if (!src_is_device) {
                 const size_t per = n_scenes == 1 ? (size_t)maxc * stride : (size_t)scene_stride;
                 CK(h->raw_stage.reserve(per * n_scenes));
-                CK(cudaMemcpyAsync(h->raw_stage.p, src, per * n_scenes, cudaMemcpyHostToDevice, st));
+                const size_t bytes = per * (n_scenes - 1) + (size_t)counts[n_scenes - 1] * stride; // no over-read
+                CK(cudaMemcpyAsync(h->raw_stage.p, src, bytes, cudaMemcpyHostToDevice, st));
                 raw = h->raw_stage.as<unsigned char>();
                 if (n_scenes == 1) scene_stride = (int64_t)per;
             }
@@ -1182,6 +1190,8 @@ int ampc_depth_set_batch_dev(ampc_handle *h, int32_t first_scene, int32_t n_scen
         CK(cudaStreamSynchronize(st));
         CK(h->depth_scratch.reserve((size_t)n_scenes * npx * 4));
     }
+    if (h->depth_flag.p) // an overflow reported by (or left behind by) an earlier call is not this call's
+        CK(cudaMemsetAsync(h->depth_flag.p, 0, 4, st));
     if (!h->depth_flag.p) {
         CK(h->depth_flag.reserve(4));
         CK(cudaMemset(h->depth_flag.p, 0, 4));

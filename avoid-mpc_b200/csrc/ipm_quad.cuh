@@ -1,6 +1,6 @@
 // Batched interior-point solve of the quadrotor collision-avoidance NLP (sm_100a, FP64):
 // FOUR LANES PER MPC INSTANCE, up to eight instances per warp, persistent warps that refill
-// from a queue.  Same algorithm as oracle/nlp_oracle.c: nlp_oracle_solve.
+// from a queue.  Same algorithm as the warp-per-instance kernel (ipm_solve.cuh); DESIGN.md section 2.
 //
 // Replaces ObstacleAvoidanceMPC::Solve -> casadi::nlpsol("ipopt") and the CasADi-generated
 // nlp_f / nlp_grad_f / nlp_hess_l of tools/mpc_obstacle_casadi.py

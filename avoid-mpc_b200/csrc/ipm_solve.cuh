@@ -692,7 +692,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         // region at the same time and share the instruction cache (the kernel's code is far
         // larger than it); warps that have finished have exited and no longer count
         if (SYNC)
-            __syncthreads();
+            __syncthreads_or(1); // finished warps keep voting 0 at this barrier (see the kernel)
         double eps = 0.0, f = 0.0, c_mu = 0.0, delta = 0.0;
         bool stop = false;
         // pass 0: evaluate, test convergence, update mu (IPOPT eq. (7)); if mu changed, the
@@ -902,11 +902,18 @@ ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * WARPS + warp;
-    if (b >= B || (active && active[b] == 0))
-        return;
-    const WarpLayout L(sc->N);
-    WarpCtx ctx(sc, wbase + (size_t)warp * L.total, prefix + (size_t)b * sc->n_prefix, lane);
-    solve_instance<(WARPS > 1)>(ctx, w_inout + (size_t)b * (10 + 14 * sc->N), info + b);
+    if (!(b >= B || (active && active[b] == 0))) {
+        const WarpLayout L(sc->N);
+        WarpCtx ctx(sc, wbase + (size_t)warp * L.total, prefix + (size_t)b * sc->n_prefix, lane);
+        solve_instance<(WARPS > 1)>(ctx, w_inout + (size_t)b * (10 + 14 * sc->N), info + b);
+    }
+    // The warps of a CTA meet at a barrier at the top of every iteration.  A warp without work, or
+    // one that has finished, keeps arriving at that barrier (voting "done") until every warp of
+    // the CTA votes "done": all threads execute the same number of barriers, none is skipped by
+    // an exited warp.
+    if (WARPS > 1)
+        while (__syncthreads_or(0)) {
+        }
 }
 
 } // namespace v1

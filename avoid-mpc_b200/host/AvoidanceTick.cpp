@@ -48,7 +48,9 @@ bool AvoidanceTick::ProcessWaypoints(ObstacleList &obstacles) { // :204-235
         sites.emplace_back(mRefPath[i][0], mRefPath[i][1], mRefPath[i][2]);
     std::vector<std::vector<Eigen::Vector3d>> pts;
     std::vector<std::vector<double>> d2;
-    mMap.QueryNearestBatch(sites, mP.nearestPointNum, pts, d2); // N queries, one launch
+    // mKeyFrameMap.QueryNearest per waypoint (:214): sites outside the current frustum (typically
+    // waypoint 0, behind the camera) fall back to the key-frames; batched, at most two launches
+    mMap.QueryNearestMany(sites, mP.nearestPointNum, pts, d2);
     for (int i = 0; i < mMpcN; i++) {
         for (int j = 0; j < mP.nearestPointNum; j++) {
             if (j < (int)pts[i].size())

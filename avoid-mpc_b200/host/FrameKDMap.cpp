@@ -89,10 +89,12 @@ std::vector<pcl::PointXYZ> FrameKDMap::Download(const Cloud &c, int kind) {
 }
 
 std::vector<pcl::PointXYZ> FrameKDMap::CurrentPoints(bool edge) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
     return mCur.cloud ? Download(*mCur.cloud, edge ? 1 : 0) : std::vector<pcl::PointXYZ>();
 }
 
 void FrameKDMap::AddVertex(const Mat4 &Twb, const DepthImage &depth) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
     if (!depth.data || depth.rows < 1 || depth.cols < 1)
         throw std::runtime_error("FrameKDMap(GPU): empty depth image");
     const Mat4 Twc = mul(Twb, mP.Tbc);        // :117-119
@@ -118,6 +120,7 @@ void FrameKDMap::Upload(Cloud &c, int kind, const std::vector<pcl::PointXYZ> &pt
 }
 
 void FrameKDMap::AddClouds(const CloudPtr &cloud, const CloudPtr &edgeCloud, const Mat4 &Twc, int rowWidthHint) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
     if (ampc_cloud_set_layout(mHandle.get(), AMPC_CLOUD_OBSTACLE, rowWidthHint) != AMPC_OK)
         die(mHandle.get(), "ampc_cloud_set_layout");
     std::shared_ptr<Cloud> c = NewCloud();
@@ -182,9 +185,93 @@ void FrameKDMap::SearchFrames(const std::vector<const Frame *> &frames, const Ei
     }
 }
 
+void FrameKDMap::SearchFramesMany(const std::vector<const Frame *> &frames, const std::vector<Eigen::Vector3d> &ps,
+                                  int k, int kind, std::vector<std::vector<std::vector<Eigen::Vector3d>>> &pts,
+                                  std::vector<std::vector<std::vector<double>>> &d2) {
+    const int F = (int)frames.size(), Q = (int)ps.size();
+    pts.assign(Q, std::vector<std::vector<Eigen::Vector3d>>(F));
+    d2.assign(Q, std::vector<std::vector<double>>(F));
+    if (F == 0 || Q == 0 || k <= 0)
+        return;
+    std::vector<int32_t> scene_of(F), cnt((size_t)F * Q);
+    std::vector<double> q((size_t)3 * F * Q), dd((size_t)F * Q * k), pp((size_t)F * Q * k * 3);
+    for (int f = 0; f < F; ++f) {
+        scene_of[f] = frames[f]->cloud->slot;
+        for (int i = 0; i < Q; ++i) {
+            double *d = &q[((size_t)f * Q + i) * 3];
+            d[0] = ps[i].x(), d[1] = ps[i].y(), d[2] = ps[i].z();
+        }
+    }
+    if (ampc_knn_batch(mHandle.get(), kind, F, scene_of.data(), q.data(), Q, k, nullptr, dd.data(), pp.data(),
+                       cnt.data()) != AMPC_OK)
+        die(mHandle.get(), "ampc_knn_batch");
+    for (int f = 0; f < F; ++f) {
+        if (frames[f]->cloud->count[kind] <= k)
+            continue; // n < k asks for n and gets none; n == k gets none
+        for (int i = 0; i < Q; ++i)
+            for (int j = 0; j < cnt[(size_t)f * Q + i]; ++j) {
+                const double *c = &pp[(((size_t)f * Q + i) * k + j) * 3];
+                pts[i][f].emplace_back(c[0], c[1], c[2]);
+                d2[i][f].push_back(dd[((size_t)f * Q + i) * k + j]);
+            }
+    }
+}
+
+void FrameKDMap::QueryNearestMany(const std::vector<Eigen::Vector3d> &points, int k,
+                                  std::vector<std::vector<Eigen::Vector3d>> &out,
+                                  std::vector<std::vector<double>> &distances, bool queryEdge) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
+    const int Q = (int)points.size();
+    out.assign(Q, {});
+    distances.assign(Q, {});
+    const int kind = queryEdge ? AMPC_CLOUD_EDGE : AMPC_CLOUD_OBSTACLE;
+    std::vector<int> fast, slow;
+    const bool cur_ok = mHaveCur && mCur.cloud->count[kind] >= k;
+    for (int i = 0; i < Q; ++i)
+        (cur_ok && PtIsInFrame(points[i], mCur.Twc) ? fast : slow).push_back(i);
+    if (!fast.empty()) { // fast path (:329-346)
+        std::vector<Eigen::Vector3d> sites;
+        for (int i : fast) sites.push_back(points[i]);
+        std::vector<std::vector<Eigen::Vector3d>> o;
+        std::vector<std::vector<double>> d;
+        QueryNearestBatch(sites, k, o, d, queryEdge);
+        for (size_t j = 0; j < fast.size(); ++j)
+            out[fast[j]] = o[j], distances[fast[j]] = d[j];
+    }
+    if (!slow.empty()) { // slow path (:347-375): every frame of the query vector, merged by distance
+        std::vector<Eigen::Vector3d> sites;
+        for (int i : slow) sites.push_back(points[i]);
+        std::vector<std::vector<std::vector<Eigen::Vector3d>>> pts;
+        std::vector<std::vector<std::vector<double>>> d2;
+        SearchFramesMany(QueryVector(), sites, k, kind, pts, d2);
+        for (size_t j = 0; j < slow.size(); ++j) {
+            std::vector<std::pair<double, Eigen::Vector3d>> all;
+            for (size_t f = 0; f < pts[j].size(); ++f)
+                for (size_t e = 0; e < pts[j][f].size(); ++e)
+                    all.emplace_back(d2[j][f][e], pts[j][f][e]);
+            std::stable_sort(all.begin(), all.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+            for (int e = 0; e < k && e < (int)all.size(); ++e) {
+                out[slow[j]].push_back(all[e].second);
+                distances[slow[j]].push_back(all[e].first);
+            }
+        }
+    }
+}
+
+FrameKDMap::CloudPtr FrameKDMap::GetPtCloud() { // :489-503
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
+    auto all = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();
+    for (const Frame *f : QueryVector()) {
+        const std::vector<pcl::PointXYZ> pts = Download(*f->cloud, AMPC_CLOUD_OBSTACLE);
+        all->points.insert(all->points.end(), pts.begin(), pts.end());
+    }
+    return all;
+}
+
 void FrameKDMap::QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, int k,
                                    std::vector<std::vector<Eigen::Vector3d>> &out,
                                    std::vector<std::vector<double>> &distances, bool queryEdge) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
     const int Q = (int)points.size();
     out.assign(Q, {});
     distances.assign(Q, {});
@@ -211,6 +298,7 @@ void FrameKDMap::QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, i
 
 void FrameKDMap::QueryNearest(const Eigen::Vector3d &point, int k, std::vector<Eigen::Vector3d> &out,
                               std::vector<double> &distances, bool queryEdge) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
     out.clear();
     distances.clear();
     const int kind = queryEdge ? AMPC_CLOUD_EDGE : AMPC_CLOUD_OBSTACLE;
@@ -263,6 +351,7 @@ bool FrameKDMap::DroneBehindPts(const Mat4 &Twc, const Frame &frame) { // :233-2
     std::vector<std::vector<Eigen::Vector3d>> pts;
     std::vector<std::vector<double>> d2;
     if (ptsCount > 0) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
         // SearchForNearest(twb, ptsCount) on that frame: nothing when the frame holds exactly ptsCount points
         std::vector<int32_t> cnt(1);
         std::vector<double> q = {twb.x(), twb.y(), twb.z()}, dd(ptsCount), pp(3 * (size_t)ptsCount);
@@ -296,6 +385,7 @@ void FrameKDMap::ProcessKeyframes() { // body of KeyframeThreadWorker, :446-487
     if (!mHaveCur)
         return;
     if (mKeyFrames.empty()) {
+    std::lock_guard<std::recursive_mutex> lock(mMtxKdTree);
         InsertKeyFrame();
         return;
     }

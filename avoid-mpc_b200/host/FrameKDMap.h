@@ -20,6 +20,7 @@
 #include <array>
 #include <deque>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 using Mat4 = std::array<double, 16>; // row-major homogeneous transform
@@ -56,10 +57,19 @@ public:
                       std::vector<Eigen::Vector3d> &out, std::vector<double> &distances,
                       bool queryEdge = false);
     double GetNearestDistance(const Eigen::Vector3d &point);
-    // batched current-frame query used by the tick loop: Q query sites, one launch
+    // batched current-frame query: Q query sites, one launch, the current frame only
     void QueryNearestBatch(const std::vector<Eigen::Vector3d> &points, int nearestPointCount,
                            std::vector<std::vector<Eigen::Vector3d>> &out,
                            std::vector<std::vector<double>> &distances, bool queryEdge = false);
+    // Q query sites with QueryNearest's semantics for EACH of them (fast path on the current frame
+    // if the site projects into its frustum and the cloud has >= k points, else all frames of the
+    // query vector merged by distance, :329-376): at most two launches -- the in-frame sites on the
+    // current frame, the others over (frames x sites).  What ProcessWaypoints needs (:204-235).
+    void QueryNearestMany(const std::vector<Eigen::Vector3d> &points, int nearestPointCount,
+                          std::vector<std::vector<Eigen::Vector3d>> &out,
+                          std::vector<std::vector<double>> &distances, bool queryEdge = false);
+    // all points of the query vector's Obstacle clouds, current frame first (GetPtCloud, :489-503)
+    CloudPtr GetPtCloud();
     // key-frames (the reference runs ProcessKeyframes' body in a detached thread every 30 ms)
     void ProcessKeyframes();
     void InsertKeyFrame();
@@ -91,6 +101,13 @@ private:
     std::vector<const Frame *> QueryVector() const; // UpdateQueryVector (:65-75)
     void SearchFrames(const std::vector<const Frame *> &frames, const Eigen::Vector3d &p, int k, int kind,
                       std::vector<std::vector<Eigen::Vector3d>> &pts, std::vector<std::vector<double>> &d2);
+    // the same for several sites in one launch: result [site][frame]
+    void SearchFramesMany(const std::vector<const Frame *> &frames, const std::vector<Eigen::Vector3d> &ps, int k,
+                          int kind, std::vector<std::vector<std::vector<Eigen::Vector3d>>> &pts,
+                          std::vector<std::vector<std::vector<double>>> &d2);
+    // mMtxKdTree of the reference (:48,328,365,406,425,443,491): tree swap, queries and the
+    // key-frame pass exclude each other; recursive because the public entries call each other
+    mutable std::recursive_mutex mMtxKdTree;
     std::shared_ptr<ampc_handle> mHandle;
     MapParams mP;
     std::shared_ptr<std::vector<int>> mFreeSlots; // outlives every Cloud

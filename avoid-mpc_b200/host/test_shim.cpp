@@ -185,6 +185,27 @@ int main(int argc, char **argv) {
         want = brute(ahead, {3});
         for (int j = 0; j < 8; ++j) CHECK(dist[j] == want[j]);
         CHECK(kmap.GetNearestDistance(ahead) == std::sqrt(brute(ahead, {3, 0, 1})[0]));
+        // QueryNearestMany == QueryNearest site by site, in and out of the frustum mixed (what
+        // ProcessWaypoints needs: a waypoint behind the camera must see the key-frames' obstacles)
+        {
+            const std::vector<Eigen::Vector3d> sites = {behind, ahead, side, Eigen::Vector3d(14, -0.3, 1.6),
+                                                        Eigen::Vector3d(-55, 0.1, 1.0)};
+            std::vector<std::vector<Eigen::Vector3d>> mo;
+            std::vector<std::vector<double>> md;
+            kmap.QueryNearestMany(sites, 8, mo, md);
+            int n_slow = 0;
+            for (size_t i = 0; i < sites.size(); ++i) {
+                kmap.QueryNearest(sites[i], 8, out, dist);
+                CHECK(md[i].size() == dist.size() && dist.size() == 8);
+                for (int j = 0; j < 8; ++j)
+                    CHECK(md[i][j] == dist[j] && mo[i][j].x() == out[j].x() && mo[i][j].z() == out[j].z());
+                n_slow += !kmap.PtIsInFrame(sites[i], mat(-50, 0, 1.5));
+            }
+            CHECK(n_slow == 3);
+            // the nearest obstacle of `behind` lives in key-frame 0, not in the current frame
+            CHECK(md[0][0] == brute(behind, {3, 0, 1})[0] && md[0][0] < brute(behind, {3})[0]);
+            CHECK(kmap.GetPtCloud()->points.size() == 9000);
+        }
         // ProcessKeyframes: the last key-frame keeps only its points farther than 0.1 m from the
         // current cloud, then the current frame becomes a key-frame (:462-486)
         auto cur = std::make_shared<pcl::PointCloud<pcl::PointXYZ>>();

@@ -238,3 +238,46 @@ def test_sort_layout_round_equals_unorganised_round():
         res.append((W, info["cost"].copy(), replan.copy()))
         h.close()
     assert (res[0][0] == res[1][0]).all() and (res[0][1] == res[1][1]).all() and (res[0][2] == res[1][2]).all()
+
+
+def test_one_row_organised_cloud_with_a_wide_row_hint():
+    """A row hint wider than the cloud is tall (here: ONE image row of 20000 records in slots sized
+    for 65536 points) would need ceil(w/8) = 2500 tiles of 8 points against 2112 tile slots; such a
+    scene must fall back to the linear tiling instead of writing boxes past its slots."""
+    Q, k, npts = 20, 16, 20000
+    h = A.Handle(N=Q, K=k, max_batch=3, max_points=65536)
+    h.cloud_set_layout(20000)
+    clouds = [S.forest_cloud(40 + s, npts)[0] for s in range(3)]
+    for s, c in enumerate(clouds):
+        h.cloud_set(s, c)
+    queries = np.stack([S.states(40 + s, Q)[1][:, :3] for s in range(3)])
+    _check(h, clouds, queries, k)      # scene 1's boxes would have been overwritten by scene 0's
+    # a hint that fits (250 columns x 80 rows) on the same handle still gives the same answers
+    h.cloud_set_layout(250)
+    for s, c in enumerate(clouds):
+        h.cloud_set(s, c)
+    _check(h, clouds, queries, k)
+    h.close()
+
+
+def test_cloud_set_batch_reads_only_each_scenes_own_points():
+    """ampc_cloud_set_batch on a buffer that ends right after the LAST scene's points (shorter than
+    the largest scene): counts[s] records of scene s are all the call may read."""
+    import ctypes
+    Q, k = 8, 4
+    counts = np.array([3000, 4096, 1000], dtype=np.int32)
+    stride = 4096 * 16
+    h = A.Handle(N=Q, K=k, max_batch=3, max_points=4096)
+    clouds = [S.random_cloud(60 + s, int(n)) for s, n in enumerate(counts)]
+    # page-aligned allocation whose last valid byte is the last point of the last scene
+    nbytes = 2 * stride + int(counts[2]) * 16
+    buf = np.zeros(nbytes, dtype=np.uint8)
+    for s, c in enumerate(clouds):
+        raw = np.ascontiguousarray(c, dtype=np.float32).view(np.uint8).ravel()
+        buf[s * stride:s * stride + raw.size] = raw
+    rc = h.L.ampc_cloud_set_batch(h.h, A.capi.CLOUD_OBSTACLE, 0, 3, buf.ctypes.data_as(ctypes.c_void_p),
+                                  counts.ctypes.data, stride, 16)
+    assert rc == 0
+    q = np.stack([np.random.default_rng(s).uniform(-1, 1, (Q, 3)) for s in range(3)])
+    _check(h, clouds, q, k)
+    h.close()
