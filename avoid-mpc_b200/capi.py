@@ -31,6 +31,7 @@ SYMBOLS = [
     "ampc_best_of", "ampc_best_of_dev", "ampc_launch_count", "ampc_stream", "ampc_synchronize",
     "ampc_profile_enable", "ampc_profile_get",
     "ampc_cloud_get", "ampc_set_camera", "ampc_depth_set_batch", "ampc_depth_set_batch_dev",
+    "ampc_guess_round_batch", "ampc_guess_round_batch_dev", "ampc_measure_fp64_peak",
 ]
 
 
@@ -129,6 +130,10 @@ def lib():
                                           _vp, _vp, _vp, _vp, _vp]
         L.ampc_best_of.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp]
         L.ampc_best_of_dev.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
+        L.ampc_guess_round_batch.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp, _vp]
+        L.ampc_guess_round_batch_dev.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_double, _vp, _vp, _vp,
+                                                 _vp, _vp]
+        L.ampc_measure_fp64_peak.argtypes = [_vp, C.POINTER(C.c_double)]
         L.ampc_launch_count.restype = C.c_int64
         L.ampc_launch_count.argtypes = [_vp]
         L.ampc_stream.restype = _vp
@@ -392,6 +397,33 @@ class Handle:
         best = np.empty(n_scenes, dtype=np.float64)
         self._ck(self.L.ampc_best_of(self.h, n_scenes, G, info.ctypes.data, arg.ctypes.data, best.ctypes.data))
         return arg, best
+
+    def guess_round(self, x0, ref, w0, G, pos_x=None, speed=10.0):
+        """Edge-tree guesses + best-of-G (BASELINE config C2): x0 (S,10), ref (S,N,10), w0 (S*G, n_w).
+        Returns (w, info, argmin, best_cost)."""
+        x0 = _f64(x0).reshape(-1, 10)
+        Sn = x0.shape[0]
+        ref = _f64(ref, (Sn, self.N, 10))
+        w = np.array(w0, dtype=np.float64).reshape(Sn * G, self.n_w).copy()
+        px = None if pos_x is None else _f64(pos_x, (Sn,))
+        info = np.zeros(Sn * G, dtype=INFO_DTYPE)
+        arg = np.empty(Sn, dtype=np.int32)
+        best = np.empty(Sn, dtype=np.float64)
+        self._ck(self.L.ampc_guess_round_batch(self.h, Sn, G, x0.ctypes.data, ref.ctypes.data, _ptr(px), speed,
+                                               w.ctypes.data, info.ctypes.data, arg.ctypes.data, best.ctypes.data))
+        return w, info, arg, best
+
+    def guess_round_dev(self, n_scenes, G, x0_dev, ref_dev, w_dev, info_dev=None, argmin_dev=None, best_dev=None,
+                        pos_x_dev=None, speed=10.0, stream=None):
+        self._ck(self.L.ampc_guess_round_batch_dev(self.h, n_scenes, G, _ptr(x0_dev), _ptr(ref_dev), _ptr(pos_x_dev),
+                                                   speed, _ptr(w_dev), _ptr(info_dev), _ptr(argmin_dev),
+                                                   _ptr(best_dev), stream))
+
+    def measure_fp64_peak(self):
+        """FP64 FMA throughput of the device in TFLOP/s (hand-written dependent-FMA-chain kernel)."""
+        v = C.c_double()
+        self._ck(self.L.ampc_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     def best_of_dev(self, n_scenes, G, info_dev, argmin_dev, best_dev, stream=None):
         self._ck(self.L.ampc_best_of_dev(self.h, n_scenes, G, _ptr(info_dev), _ptr(argmin_dev), _ptr(best_dev), stream))

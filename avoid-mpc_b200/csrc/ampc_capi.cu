@@ -78,6 +78,7 @@ struct ampc_handle {
     DevBuf queries, prefix, w, info, knn_idx, knn_d2, knn_cnt, knn_pts, scene_of, x0, ref, posx, replan;
     DevBuf ws_d, ws_i, ws_counter;
     DevBuf bo_arg, bo_cost;
+    DevBuf gs_sites, gs_nb, gs_epts, gs_ecnt, gs_q0; // Edge-tree guess round (ampc_guess_round_batch)
     DevBuf tk_active, tk_q0, tk_d1, tk_c1, tk_ep, tk_ec, tk_ed, tk_safe, tk_rounds; // tick loop
     int64_t launches = 0;
     std::string err;
@@ -257,6 +258,78 @@ __global__ void replan_kernel(int B, int Q, int k, const double *dist2, const in
             flag = 1;
     }
     need_replan[b] = flag;
+}
+
+// ---- Edge-tree initial guesses (BASELINE config C2; PlanWapionts generalised, :259-281) ------
+// Query sites of scene s: the N-1 waypoints 1..N-1 shared by all guesses, then the G guess
+// positions for waypoint 0.  Guess g = g-th nearest Edge point of waypoint 0; beyond the number of
+// Edge points the waypoint stays where it is.
+__global__ void guess_sites_kernel(int n_scenes, int N, int G, const double *ref, const double *epts,
+                                   const int32_t *ecnt, double *sites) {
+    const int s = blockIdx.x;
+    const int Qp = N - 1 + G;
+    const double *r = ref + (int64_t)s * N * 10;
+    for (int i = threadIdx.x; i < Qp; i += blockDim.x) {
+        double *o = sites + ((int64_t)s * Qp + i) * 3;
+        if (i < N - 1) {
+            o[0] = r[10 * (i + 1)], o[1] = r[10 * (i + 1) + 1], o[2] = r[10 * (i + 1) + 2];
+        } else {
+            const int g = i - (N - 1);
+            const double *e = g < ecnt[s] ? epts + ((int64_t)s * G + g) * 3 : r;
+            o[0] = e[0], o[1] = e[1], o[2] = e[2];
+        }
+    }
+}
+// prefix of instance b = s*G + g: [x0_s | ref_s with waypoint 0 at guess g | obst | target]; the
+// neighbour block of stage 0 comes from the guess's own query, stages 1.. from the shared ones
+__global__ void guess_pack_kernel(int n_scenes, int N, int K, int G, const double *x0, const double *ref,
+                                  const double *pos_x, double speed, double T, const double *sites,
+                                  const double *nb /* [s][N-1+G][K][3] */, double *prefix, int n_prefix) {
+    const int b = blockIdx.x, s = b / G, g = b - s * G;
+    const int Qp = N - 1 + G;
+    double *p = prefix + (int64_t)b * n_prefix;
+    const double *r = ref + (int64_t)s * N * 10;
+    const double *site0 = sites + ((int64_t)s * Qp + (N - 1 + g)) * 3;
+    for (int i = threadIdx.x; i < 10; i += blockDim.x)
+        p[i] = x0[(int64_t)s * 10 + i];
+    for (int i = threadIdx.x; i < 10 * N; i += blockDim.x)
+        p[10 + i] = i < 3 ? site0[i] : r[i];
+    const double *nbs = nb + (int64_t)s * Qp * K * 3;
+    for (int i = threadIdx.x; i < 3 * K * N; i += blockDim.x) {
+        const int k = i / (3 * K), e = i - k * 3 * K;
+        const int q = k == 0 ? N - 1 + g : k - 1;
+        p[10 + 10 * N + i] = nbs[(int64_t)q * K * 3 + e];
+    }
+    if (threadIdx.x < 10) { // target rule, :250-255
+        const int i = threadIdx.x;
+        double v = r[10 * (N - 1) + i];
+        if (N == 1 && i < 3)
+            v = site0[i];
+        if (i == 0) {
+            const double px = pos_x ? pos_x[s] : x0[(int64_t)s * 10];
+            double dX = speed * T - fmax(0.0, v - px);
+            dX = fmax(0.0, dX);
+            v += dX;
+        }
+        if (i == 1)
+            v = 0.0;
+        p[10 + 10 * N + 3 * K * N + i] = v;
+    }
+}
+
+// ---- FP64 FMA peak of the device, measured: 8 independent dependent-FMA chains per thread,
+// enough resident warps to cover the pipe latency (the denominator of the solve kernels' roofline)
+__global__ void __launch_bounds__(256) fp64_fma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+        }
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
 __global__ void best_of_kernel(int n_scenes, int G, const SolveOut *info, int32_t *argmin,
@@ -768,7 +841,7 @@ void ampc_destroy(ampc_handle *h) {
                      &h->depth_scratch, &h->depth_flag, &h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
-                     &h->ws_i, &h->ws_counter, &h->quad_ws, &h->quad_counter, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
+                     &h->ws_i, &h->ws_counter, &h->quad_ws, &h->quad_counter, &h->gs_sites, &h->gs_nb, &h->gs_epts, &h->gs_ecnt, &h->gs_q0, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
                      &h->tk_c1, &h->tk_ep, &h->tk_ec, &h->tk_ed, &h->tk_safe, &h->tk_rounds};
     for (DevBuf *b : all)
         b->release();
@@ -1456,6 +1529,121 @@ int ampc_last_prefix_dev(ampc_handle *h, const double **p) {
 }
 
 // ---- best-of-G ----------------------------------------------------------------
+int ampc_guess_round_batch_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const double *x0_dev,
+                               const double *ref_dev, const double *pos_x_dev, double speed,
+                               double *w_inout_dev, ampc_solve_info *info_dev, int32_t *argmin_dev,
+                               double *best_cost_dev, void *stream) {
+    if (!h) return AMPC_ERR_INVALID;
+    if (n_scenes < 1 || G < 1 || G > KNN_KMAX) return fail(h, AMPC_ERR_INVALID, "need n_scenes >= 1 and 1 <= G <= 32");
+    int rc = check_batch(h, n_scenes * G);
+    if (rc) return rc;
+    if ((rc = check_kind(h, AMPC_CLOUD_OBSTACLE)) || (rc = check_kind(h, AMPC_CLOUD_EDGE))) return rc;
+    if (n_scenes > h->cfg.max_scenes) return fail(h, AMPC_ERR_CAPACITY, "n_scenes exceeds ampc_config.max_scenes");
+    if (!x0_dev || !ref_dev || !w_inout_dev) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    if (h->cfg.K < 1) return fail(h, AMPC_ERR_INVALID, "round needs K >= 1");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = h->cfg.N, K = h->cfg.K, Qp = N - 1 + G, B = n_scenes * G;
+    CK(h->gs_sites.reserve((size_t)n_scenes * Qp * 3 * 8));
+    CK(h->gs_nb.reserve((size_t)n_scenes * Qp * K * 3 * 8));
+    CK(h->gs_epts.reserve((size_t)n_scenes * G * 3 * 8));
+    CK(h->gs_ecnt.reserve((size_t)n_scenes * 4));
+    CK(h->gs_q0.reserve((size_t)n_scenes * 3 * 8));
+    // (1) the G nearest Edge points of waypoint 0 of every scene
+    tick_site0_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(n_scenes, N, ref_dev, h->gs_q0.as<double>());
+    h->launches++;
+    CK(cudaGetLastError());
+    int slot;
+    if ((rc = prof_begin(h, SEC_KNN, st, &slot))) return rc;
+    rc = launch_knn(h, AMPC_CLOUD_EDGE, n_scenes, nullptr, h->gs_q0.as<double>(), 1, G, h->knn_idx.as<int32_t>(),
+                    h->knn_d2.as<double>(), h->gs_ecnt.as<int32_t>(), h->gs_epts.as<double>(), (int64_t)G * 3,
+                    (int64_t)G * 3, st);
+    if (rc) return rc;
+    // (2) one Obstacle query per shared waypoint and one per guess: N-1+G per scene, not N*G
+    guess_sites_kernel<<<n_scenes, 64, 0, st>>>(n_scenes, N, G, ref_dev, h->gs_epts.as<double>(),
+                                                h->gs_ecnt.as<int32_t>(), h->gs_sites.as<double>());
+    h->launches++;
+    CK(cudaGetLastError());
+    rc = launch_knn(h, AMPC_CLOUD_OBSTACLE, n_scenes, nullptr, h->gs_sites.as<double>(), Qp, K,
+                    h->knn_idx.as<int32_t>(), h->knn_d2.as<double>(), h->knn_cnt.as<int32_t>(), h->gs_nb.as<double>(),
+                    (int64_t)Qp * K * 3, (int64_t)K * 3, st);
+    if (rc) return rc;
+    if ((rc = prof_end(h, slot, st))) return rc;
+    // (3) prefixes of the n_scenes x G instances, (4) solve, (5) best guess of every scene
+    double *prefix = h->prefix.as<double>();
+    guess_pack_kernel<<<B, 64, 0, st>>>(n_scenes, N, K, G, x0_dev, ref_dev, pos_x_dev, speed, N * h->cfg.dt,
+                                        h->gs_sites.as<double>(), h->gs_nb.as<double>(), prefix, h->n_prefix);
+    h->launches++;
+    CK(cudaGetLastError());
+    SolveOut *info = info_dev ? reinterpret_cast<SolveOut *>(info_dev) : h->info.as<SolveOut>();
+    if ((rc = prof_begin(h, SEC_SOLVE, st, &slot))) return rc;
+    rc = launch_solve(h, B, prefix, w_inout_dev, info, st);
+    if (rc) return rc;
+    if ((rc = prof_end(h, slot, st))) return rc;
+    if (argmin_dev && best_cost_dev) {
+        best_of_kernel<<<(n_scenes + 127) / 128, 128, 0, st>>>(n_scenes, G, info, argmin_dev, best_cost_dev);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return AMPC_OK;
+}
+
+int ampc_guess_round_batch(ampc_handle *h, int32_t n_scenes, int32_t G, const double *x0, const double *ref,
+                           const double *pos_x, double speed, double *w_inout, ampc_solve_info *info_out,
+                           int32_t *argmin_out, double *best_cost_out) {
+    if (!h) return AMPC_ERR_INVALID;
+    if (n_scenes < 1 || G < 1) return fail(h, AMPC_ERR_INVALID, "need n_scenes >= 1 and G >= 1");
+    int rc = check_batch(h, n_scenes * G);
+    if (rc) return rc;
+    if (!x0 || !ref || !w_inout) return fail(h, AMPC_ERR_INVALID, "null buffer");
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = h->stream;
+    const int N = h->cfg.N, B = n_scenes * G;
+    CK(cudaMemcpyAsync(h->x0.p, x0, (size_t)n_scenes * 10 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->ref.p, ref, (size_t)n_scenes * N * 10 * 8, cudaMemcpyHostToDevice, st));
+    if (pos_x) CK(cudaMemcpyAsync(h->posx.p, pos_x, (size_t)n_scenes * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->w.p, w_inout, (size_t)B * h->n_w * 8, cudaMemcpyHostToDevice, st));
+    rc = ampc_guess_round_batch_dev(h, n_scenes, G, h->x0.as<double>(), h->ref.as<double>(),
+                                    pos_x ? h->posx.as<double>() : nullptr, speed, h->w.as<double>(),
+                                    reinterpret_cast<ampc_solve_info *>(h->info.p), h->bo_arg.as<int32_t>(),
+                                    h->bo_cost.as<double>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(w_inout, h->w.p, (size_t)B * h->n_w * 8, cudaMemcpyDeviceToHost, st));
+    if (info_out) CK(cudaMemcpyAsync(info_out, h->info.p, (size_t)B * sizeof(SolveOut), cudaMemcpyDeviceToHost, st));
+    if (argmin_out) CK(cudaMemcpyAsync(argmin_out, h->bo_arg.p, (size_t)n_scenes * 4, cudaMemcpyDeviceToHost, st));
+    if (best_cost_out) CK(cudaMemcpyAsync(best_cost_out, h->bo_cost.p, (size_t)n_scenes * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMPC_OK;
+}
+
+int ampc_measure_fp64_peak(ampc_handle *h, double *tflops_out) {
+    if (!h || !tflops_out) return AMPC_ERR_INVALID;
+    CK(cudaSetDevice(h->cfg.device));
+    const int blocks = h->n_sm * 8, threads = 256, iters = 4096;
+    DevBuf out;
+    CK(out.reserve((size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) { // first repetition = warm-up
+        CK(cudaEventRecord(e0, h->stream));
+        fp64_fma_peak_kernel<<<blocks, threads, 0, h->stream>>>(out.as<double>(), iters, 0.999999, 1e-6);
+        CK(cudaEventRecord(e1, h->stream));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    h->launches += 4;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    out.release();
+    const double flop = 2.0 * 64.0 * iters * (double)blocks * threads; // 64 FMA per thread per iteration
+    *tflops_out = flop / (best * 1e-3) / 1e12;
+    return AMPC_OK;
+}
+
 int ampc_best_of_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_info *info_dev,
                      int32_t *argmin_dev, double *best_cost_dev, void *stream) {
     if (!h) return AMPC_ERR_INVALID;

@@ -1,12 +1,19 @@
 #!/usr/bin/env python
 """Headline benchmark: MPC solves/sec at N=20, K=16 obstacle terms/stage, 50k-point clouds.
 
-One "step" = one round of the reference's control tick for a batch of independent MPC
-instances (src/AvoidanceStateMachine.cpp:328-344): Q=N k-NN queries of K neighbours on each
-instance's Obstacle cloud + prefix packing + one NLP solve to convergence (tol 1e-8).
+One "solve" = one round of the reference's control tick for one MPC instance
+(src/AvoidanceStateMachine.cpp:328-344): the per-frame index build over the instance's 50k-point
+Obstacle cloud (the reference rebuilds its KD-trees every depth frame, src/FrameKDMap.cpp:34-52),
+Q = N k-NN queries of K neighbours, prefix packing and one NLP solve to convergence (tol 1e-8).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode ...]
 
+modes (BASELINE.json configs):
+  solves       configs[1]: batches of 1024 instances, 1xB200 (N GPUs: scene-sharded)      [default]
+  best_of      configs[2]: 4096 scenes x 32 Edge-tree initial guesses, best-cost reduction
+  scenes65536  configs[3]: 65 536 scenes sharded over the GPUs, all-gather of the costs
+  knn_sweep    configs[4]: k-NN only, 10k..1M points, achieved HBM GB/s, at N GPUs
+  cpu_c0       configs[0]: the reference's own CPU-runnable case, one thread
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
 from __future__ import annotations
@@ -17,6 +24,7 @@ import os
 import statistics
 import subprocess
 import sys
+import threading
 import time
 
 import numpy as np
@@ -27,55 +35,74 @@ sys.path.insert(0, ROOT)
 METRIC = "mpc_solves_per_sec"
 UNIT = "solves/s"
 N_H, K_NB, DT = 20, 16, 0.05
+F_ITER = (N_H - 1) * K_NB * 250 + N_H * 4275  # SURVEY.md 8d work model, FP64 flop per iteration
 
 
 def workload_name(B, npts):
     return f"batch={B} MPC instances/GPU, N={N_H}, K={K_NB} obstacle terms/stage, {npts}-pt cloud per instance"
 
 
-# ------------------------------------------------------------------ CPU arm ----
-def cpu_reference(n_scenes: int, npts: int, threads: int, steps: int = 1, warm="ref"):
-    """The reference's CPU path on host cores: tree build + 20x16-NN through the reference's own
-    KDTreeTwo/nanoflann (oracle/_ref, falls back to the C restatement) + the oracle NLP solve.
-    Returns (solves_per_sec_per_step list, description)."""
-    from concurrent.futures import ThreadPoolExecutor
+def shared_config(args, world=1):
+    """The part of `config` both arms print, key for key."""
+    return {"workload": workload_name(args.batch, args.npts), "warm_start": args.warm, "tol": args.tol,
+            "max_iter": args.max_iter, "n_gpus": world}
 
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json (measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s"
+
+
+# ------------------------------------------------------------------ CPU arm ----
+def cpu_reference(n_scenes: int, npts: int, threads: int, steps: int = 1, warm="ref", K=K_NB, tol=1e-8, max_iter=100):
+    """The reference's CPU path on the host cores, one instance per std::thread at a time
+    (oracle/cpu_arm.cpp): KDTreeTwo::InitializeNew + N x SearchForNearest through the reference's own
+    kd_tree_two.h / nanoflann (compiled into oracle/_ref) + GetRefStates packing + the oracle NLP solve.
+    Returns (solves/s per step, kind, description, stage seconds of the last step)."""
     import avoid_mpc_b200 as A
     from oracle import oracle as O
 
     D, S = A.defaults, A.synth
-    use_ref = O.ref_available()
-    O.lib()
-    if use_ref:
-        O.ref_lib()
     lb, ub = D.u_bounds()
-    opts = O.default_opts()
+    opts = O.default_opts(tol=tol, max_iter=max_iter)
     n_distinct = min(n_scenes, 48)
-    clouds = [S.forest_cloud(10_000 + s, npts)[0] for s in range(n_distinct)]
-    states = [S.states(10_000 + s, N_H) for s in range(n_distinct)]
-
-    def one(i):
-        c = clouds[i % n_distinct]
-        x0, ref, tgt = states[i % n_distinct]
-        tree = O.RefTree(c) if use_ref else O.PortTree(c)       # a1: build (every depth frame)
-        idx, d2, cnt = tree.search(ref[:, :3], K_NB)             # a2/a6: N x K-NN
-        ob = c[idx.reshape(-1), :3].astype(np.float64).reshape(N_H, K_NB, 3)
-        p = S.full_params(S.pack_prefix(x0, ref, ob, tgt))       # a7
-        w, info = O.solve(N_H, K_NB, DT, p, S.warm_start(warm, x0, ref, N_H), lb, ub, opts)  # a8
-        return info.status
-
-    rates = []
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        list(ex.map(one, range(min(n_scenes, 2 * threads))))  # warm-up
+    clouds = np.stack([S.forest_cloud(10_000 + s, npts)[0] for s in range(n_distinct)])
+    st = [S.states(10_000 + s, N_H) for s in range(n_distinct)]
+    x0, ref, tgt = (np.stack([a[i] for a in st]) for i in range(3))
+    W0 = np.stack([S.warm_start(warm, x0[i], ref[i], N_H) for i in range(n_distinct)])
+    tail = S.full_params(np.zeros(0))
+    rates, stage = [], None
+    if O.cpu_arm_available():
+        O.cpu_arm_run(min(n_scenes, 2 * threads), threads, clouds, x0, ref, tgt, tail, W0, N_H, K, DT, lb, ub, opts)
         for _ in range(steps):
-            t0 = time.perf_counter()
-            list(ex.map(one, range(n_scenes)))
-            rates.append(n_scenes / (time.perf_counter() - t0))
-    kind = "port"
-    desc = (f"{n_scenes} instances/step ({n_distinct} distinct {npts}-pt scenes), {threads} host threads; "
-            f"k-NN = {'reference nanoflann (oracle/_ref)' if use_ref else 'C restatement'} tree build + "
-            f"{N_H}x{K_NB}-NN, NLP = oracle interior-point port (CasADi/IPOPT not installable), tol 1e-8")
-    return rates, kind, desc
+            wall, _, _, stage = O.cpu_arm_run(n_scenes, threads, clouds, x0, ref, tgt, tail, W0, N_H, K, DT, lb, ub, opts)
+            rates.append(n_scenes / wall)
+        how = "native std::thread driver (oracle/cpu_arm.cpp), reference kd_tree_two.h + nanoflann for the k-NN"
+    else:  # oracle/_ref was not built (no reference tree at build time): Python-driven port
+        from concurrent.futures import ThreadPoolExecutor
+        O.lib()
+
+        def one(i):
+            j = i % n_distinct
+            tree = O.PortTree(clouds[j])
+            idx, d2, cnt = tree.search(ref[j][:, :3], K)
+            ob = clouds[j][idx.reshape(-1), :3].astype(np.float64).reshape(N_H, K, 3)
+            p = S.full_params(S.pack_prefix(x0[j], ref[j], ob, tgt[j]))
+            return O.solve(N_H, K, DT, p, W0[j], lb, ub, opts)[1].status
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, range(min(n_scenes, 2 * threads))))
+            for _ in range(steps):
+                t0 = time.perf_counter()
+                list(ex.map(one, range(n_scenes)))
+                rates.append(n_scenes / (time.perf_counter() - t0))
+        how = "Python thread pool over the C restatement (oracle/_ref missing)"
+    desc = (f"{n_scenes} instances/step ({n_distinct} distinct {npts}-pt scenes), {threads} host threads, {how}; "
+            f"per instance: tree build + {N_H}x{K}-NN + packing + oracle interior-point solve (CasADi/IPOPT not "
+            f"installable), tol {tol:g}")
+    return rates, "port", desc, (None if stage is None else [float(v) for v in stage])
 
 
 def run_reference_arm(args):
@@ -84,14 +111,16 @@ def run_reference_arm(args):
         return
     threads = os.cpu_count() or 1
     n = max(threads * 32, 256)
-    rates, kind, desc = cpu_reference(n, args.npts, threads, steps=args.warmup + args.steps)
+    rates, kind, desc, stage = cpu_reference(n, args.npts, threads, steps=args.warmup + args.steps, warm=args.warm,
+                                             tol=args.tol, max_iter=args.max_iter)
     rates = rates[args.warmup:]
     v = statistics.mean(rates)
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.batch, args.npts), "sample_instances_per_step": n},
+        "config": shared_config(args, args.gpus),
+        "run": {"sample_instances_per_step": n, "stage_seconds_summed_over_threads": stage},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -101,9 +130,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------ GPU arm ----
 class ClockSampler:
     """nvidia-smi polled every 50 ms by a reader thread that stamps each sample on arrival; the
-    samples that arrived inside [mark_begin(), mark_end()] are reported.  nvidia-smi needs about
-    a second to deliver its first sample, so it is started before the warm-up and the window
-    covers the loaded warm-up steps plus the timed region (the GPU is busy throughout)."""
+    samples that arrived inside [mark_begin(), mark_end()] are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -112,7 +139,6 @@ class ClockSampler:
         self.dev, self.p, self.rows, self.t0, self.t1, self.thread = dev, None, [], None, None, None
 
     def start(self):
-        import threading
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "50", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
@@ -142,7 +168,7 @@ class ClockSampler:
             self.p.kill()
         if self.thread:
             self.thread.join(timeout=2)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in list(self.rows):
             if self.t0 is not None and (ts < self.t0 or ts > (self.t1 or ts) + 0.05):
@@ -151,24 +177,20 @@ class ClockSampler:
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
+                sm.append(float(f[1])), mx.append(float(f[2])), pw.append(float(f[3]))
             except ValueError:
                 continue
             for nm, val in zip(names, f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons),
-                "window": "loaded warm-up steps + single-stream pass + timed region"}
+                "power_w_median": statistics.median(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons), "window": "the timed region of `value`"}
 
 
-def run_ours(args):
+def dist_setup():
     import torch
     import torch.distributed as dist
-
-    import avoid_mpc_b200 as A
-    D, S = A.defaults, A.synth
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -178,272 +200,212 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, npts = args.batch, args.npts
+    return torch, dist, world, rank, local, dev
 
-    # ---- synthetic inputs (weak scaling: B scenes per GPU, distinct per rank) ----
-    ids = list(range(rank * B, (rank + 1) * B))
-    clouds = S.forest_clouds_torch(ids, npts, dev)                      # (B, npts, 4) f32, resident
-    x0_np, ref_np, _ = S.states_batch(ids, N_H, DT)
-    w0_np = np.stack([S.warm_start(args.warm, x0_np[b], ref_np[b], N_H) for b in range(B)])
-    # `streams` independent batches in flight (a batch server keeps several ticks' batches in
-    # flight; each has its own depth frames, i.e. its own handle + clouds + outputs + stream).
-    # streams = 1 exposes every step's full latency (the solve kernel waits for its slowest
-    # instance while most SMs idle); the single-stream figure is reported alongside.
-    def make_lane():
-        hh = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=npts, device=local)
-        hh.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
-        if not args.unorganised:  # the clouds are row-major depth images: tell the index the row pitch
-            hh.cloud_set_layout(S.image_shape(npts)[0])
-        st = torch.cuda.Stream(device=dev)
-        hh.cloud_set_batch_dev(clouds, stream=torch.cuda.current_stream().cuda_stream)
+
+def fill_scenes(A, torch, h, ids, npts, dev, chunk=1024):
+    """Synthetic forest clouds of the scenes `ids` straight into the handle's slots."""
+    S = A.synth
+    st = torch.cuda.current_stream().cuda_stream
+    for s0 in range(0, len(ids), chunk):
+        c = S.forest_clouds_torch(ids[s0:s0 + chunk], npts, dev)
+        h.cloud_set_batch_dev(c, first_scene=s0, stream=st)
         torch.cuda.synchronize()
-        lane = dict(h=hh, st=st, w=torch.empty((B, 10 + 14 * N_H), dtype=torch.float64, device=dev),
-                    info=torch.zeros((B, 48), dtype=torch.uint8, device=dev),
-                    replan=torch.zeros(B, dtype=torch.int32, device=dev),
-                    costs=torch.zeros(B, dtype=torch.float64, device=dev))
-        lane["info_f64"] = lane["info"].view(torch.float64).view(B, 6)
-        return lane
+        del c
 
-    n_streams = max(1, args.streams)
-    lanes = [make_lane() for _ in range(n_streams)]
-    h = lanes[0]["h"]
-    x0 = torch.tensor(x0_np, device=dev)
-    ref = torch.tensor(ref_np, device=dev)
-    w0 = torch.tensor(w0_np, device=dev)
-    gathered = torch.zeros(B * world, dtype=torch.float64, device=dev) if world > 1 else None
+
+def solver_stats(A, info_t):
+    info = info_t.cpu().numpy().view(A.capi.INFO_DTYPE).reshape(-1)
+    it = info["iters"].astype(np.float64)
+    return info, {"converged_frac": float((info["status"] == 0).mean()),
+                  "status_counts": np.bincount(info["status"], minlength=4).tolist(),
+                  "iters_mean": float(it.mean()), "iters_p50": float(np.median(it)),
+                  "iters_p90": float(np.percentile(it, 90)), "iters_max": int(it.max())}
+
+
+def ncu_traffic(kernel_key):
+    """dram bytes (read + write) of one launch from the committed ncu --set full summary, or None."""
+    for name in ("ncu_summary_r02.json", "ncu_summary_r01.json"):
+        try:
+            m = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel_key]["metrics"]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            return sum(float(m[k]["value"]) * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum")), name
+        except Exception:
+            continue
+    return None, None
+
+
+def run_ours(args):
+    torch, dist, world, rank, local, dev = dist_setup()
+    import avoid_mpc_b200 as A
+    D, S = A.defaults, A.synth
+    B, npts, F = args.batch, args.npts, max(1, args.in_flight)
+    BF = B * F  # instances per step per GPU: F batches of the BASELINE size, each with its own scenes
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---- synthetic inputs (weak scaling: BF scenes per GPU, distinct per rank and per batch) ----
+    ids = list(range(rank * BF, (rank + 1) * BF))
+    h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=BF, max_points=npts, device=local)
+    h.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+    if not args.unorganised:  # the clouds are row-major depth images: tell the index the row pitch
+        h.cloud_set_layout(S.image_shape(npts)[0])
+    fill_scenes(A, torch, h, ids, npts, dev)
+    x0_np, ref_np, _ = S.states_batch(ids, N_H, DT)
+    w0_np = np.stack([S.warm_start(args.warm, x0_np[b], ref_np[b], N_H) for b in range(BF)])
+    x0, ref, w0 = (torch.tensor(a, device=dev) for a in (x0_np, ref_np, w0_np))
+    w = torch.empty_like(w0)
+    info = torch.zeros((BF, 48), dtype=torch.uint8, device=dev)
+    info_f64 = info.view(torch.float64).view(BF, 6)
+    replan = torch.zeros(BF, dtype=torch.int32, device=dev)
+    costs = torch.zeros(BF, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(BF * world, dtype=torch.float64, device=dev) if world > 1 else None
     torch.cuda.synchronize()
 
-    def step(lane):
-        hh, st = lane["h"], lane["st"]
-        with torch.cuda.stream(st):
-            lane["w"].copy_(w0, non_blocking=True)
-            # a new depth frame per solve (the reference rebuilds its KD-trees every frame,
-            # src/FrameKDMap.cpp:34-52): index build = the one streaming pass over the cloud
-            hh.cloud_index_dev(0, B, stream=st.cuda_stream)
-            hh.round_dev(B, x0, ref, lane["w"], info_dev=lane["info"], replan_dev=lane["replan"], speed=D.SPEED,
-                         safety_distance=D.SAFETY_DISTANCE, stream=st.cuda_stream)
-            if world > 1:  # per-instance best-cost exchange: the only collective of the path
-                lane["costs"].copy_(lane["info_f64"][:, 0])
-                dist.all_gather_into_tensor(gathered, lane["costs"])
+    def step(n=BF):
+        w[:n].copy_(w0[:n], non_blocking=True)
+        # a new depth frame per solve: the index build is the one streaming pass over the clouds
+        h.cloud_index_dev(0, n, stream=stream)
+        h.round_dev(n, x0, ref, w, info_dev=info, replan_dev=replan, speed=D.SPEED,
+                    safety_distance=D.SAFETY_DISTANCE, stream=stream)
+        if world > 1 and n == BF:  # per-instance best-cost exchange: the only collective of the path
+            costs.copy_(info_f64[:, 0])
+            dist.all_gather_into_tensor(gathered, costs)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(lanes_used, steps):
-        """K steps round-robin over the lanes; device time from a start event every lane waits on
-        to an end event recorded after every lane has finished."""
-        main = torch.cuda.current_stream()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    def timed(steps, n=BF):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
-        start.record(main)
-        for ln in lanes_used:
-            ln["st"].wait_event(start)
-        for i in range(steps):
-            ln = lanes_used[i % len(lanes_used)]
-            sev[i][0].record(ln["st"])
-            step(ln)
-            sev[i][1].record(ln["st"])
-        for ln in lanes_used:
-            main.wait_stream(ln["st"])
-        end.record(main)
+        e0.record()
+        for _ in range(steps):
+            step(n)
+        e1.record()
         barrier()
-        return start.elapsed_time(end), [a.elapsed_time(b) for a, b in sev]
+        return e0.elapsed_time(e1)
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        for ln in lanes:
-            step(ln)
+        step()
     barrier()
-    # keep the GPU loaded (untimed; the same count on every rank) until the clock sampler has
-    # something to report, then go straight into the measured passes
+    if rank == 0:  # nvidia-smi needs about a second for its first sample: keep the GPU loaded meanwhile
+        t_end = time.perf_counter() + 1.2
+    n_load = 0
+    while True:
+        step()
+        n_load += 1
+        flag = torch.tensor([1.0 if (rank == 0 and time.perf_counter() < t_end) else 0.0], device=dev)
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if flag.item() == 0.0:
+            break
+    barrier()
+    # ---- the timed region: exactly K steps, device time, max over ranks ----
+    h.profile_enable(True)
+    l0 = h.launch_count()
     sampler.mark_begin()
-    for _ in range(args.load_rounds):
-        for ln in lanes:
-            step(ln)
-    barrier()
-    # single-stream pass: one batch in flight, every kernel runs alone -> the per-kernel times used
-    # for the roofline objects (under several streams a kernel's duration includes time-sharing)
-    lanes[0]["h"].profile_enable(True)
-    n_single = max(3, args.steps // 2)
-    single_ms, single_step_ms = timed(lanes[:1], n_single)
-    prof1 = lanes[0]["h"].profile_get()
-    lanes[0]["h"].profile_enable(False)
-    for ln in lanes:
-        ln["h"].profile_enable(True)
-    l0 = sum(ln["h"].launch_count() for ln in lanes)
-    total_ms, step_ms = timed(lanes, args.steps)
-    launches = sum(ln["h"].launch_count() for ln in lanes) - l0
-    ov = {"index": 0.0, "knn": 0.0, "solve": 0.0, "n": 0}
-    for ln in lanes:
-        prof = ln["h"].profile_get()
-        for kk in ("index", "knn", "solve"):
-            ov[kk] += prof[kk][0]
-        ov["n"] += prof["solve"][1]
-        ln["h"].profile_enable(False)
-    index_ms, knn_ms, solve_ms = prof1["index"][0], prof1["knn"][0], prof1["solve"][0]
-    rounds = prof1["solve"][1]
+    total_ms = timed(args.steps)
+    sampler.mark_end()
+    launches = h.launch_count() - l0
+    prof = h.profile_get()
+    h.profile_enable(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    info = lanes[0]["info"]
-    replan = lanes[0]["replan"]
-    w = lanes[0]["w"]
-    info_np = info.cpu().numpy().view(A.capi.INFO_DTYPE).reshape(B)
-    value = world * B * args.steps / (total_ms * 1e-3)
-    single_value = world * B * n_single / (single_ms * 1e-3)
+    value = world * BF * args.steps / (total_ms * 1e-3)
+    info_np, sstats = solver_stats(A, info)
+    sstats["need_replan_frac"] = float(replan.float().mean().item())
+    index_ms, knn_ms, solve_ms = (prof[k][0] / max(prof[k][1], 1) for k in ("index", "knn", "solve"))
 
-    # ---- end to end through the host-buffer C-ABI: clouds + states from pinned host memory,
-    #      trajectories/costs/status back to host, every step ----
-    clouds_h = torch.empty(clouds.shape, dtype=torch.float32, pin_memory=True)
-    clouds_h.copy_(clouds)
-    x0_h = torch.tensor(x0_np).pin_memory()
-    ref_h = torch.tensor(ref_np).pin_memory()
-    w0_h = torch.tensor(w0_np).pin_memory()
-    # two host threads, each driving its own handle through the synchronous host-buffer calls:
-    # the upload of one batch's clouds overlaps the k-NN + solve of the other (ctypes releases
-    # the GIL).  Every step still copies all of its inputs in and all of its results out.
-    from concurrent.futures import ThreadPoolExecutor
-    e2e_lanes = lanes[:2]
-    for ln in e2e_lanes:
-        ln["w_h"] = torch.empty_like(w0_h).pin_memory()
-        ln["info_h"] = torch.zeros((B, 48), dtype=torch.uint8).pin_memory()
-        ln["replan_h"] = torch.zeros(B, dtype=torch.int32).pin_memory()
-    w_h, info_h, replan_h = e2e_lanes[0]["w_h"], e2e_lanes[0]["info_h"], e2e_lanes[0]["replan_h"]
-    torch.cuda.synchronize()
+    # ---- one batch of the BASELINE size alone (latency view; the warp-per-instance kernel) ----
+    for _ in range(3):
+        step(B)
+    h.profile_enable(True)
+    n_single = max(5, args.steps)
+    single_ms = timed(n_single, B)
+    prof1 = h.profile_get()
+    h.profile_enable(False)
+    info1_np, s1 = solver_stats(A, info[:B])
+    single = {"value": world * B * n_single / (single_ms * 1e-3), "unit": UNIT, "ms_per_batch": single_ms / n_single,
+              "stage_ms": {k: prof1[k][0] / max(prof1[k][1], 1) for k in ("index", "knn", "solve")},
+              "note": "one 1024-instance batch in flight: the batch waits for its slowest instance "
+                      "(iterations p50 %d, max %d)" % (s1["iters_p50"], s1["iters_max"])}
 
-    def e2e_step(ln):
-        ln["w_h"].copy_(w0_h)
-        ln["h"].cloud_set_batch(clouds_h)                             # H2D of this step's clouds (+ index build)
-        ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
-                                safety_distance=D.SAFETY_DISTANCE)    # H2D states, k-NN, solve, D2H results
-
-    e2e_steps = max(4, min(args.steps, 10))
-    with ThreadPoolExecutor(max_workers=len(e2e_lanes)) as ex:
-        list(ex.map(e2e_step, [e2e_lanes[i % len(e2e_lanes)] for i in range(2 * len(e2e_lanes))]))
-        barrier()
-        t0 = time.perf_counter()
-        list(ex.map(e2e_step, [e2e_lanes[i % len(e2e_lanes)] for i in range(e2e_steps)]))
-        barrier()
-        e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(t.item())
-    h2d = clouds_h.numel() * 4 + (x0_h.numel() + ref_h.numel() + w_h.numel()) * 8
-    d2h = w_h.numel() * 8 + info_h.numel() + replan_h.numel() * 4
+    e2e = e2e_leg(A, torch, dist, dev, local, world, args)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the HBM-bound kernel (k-NN scan): SURVEY.md §8d algorithmic bytes ----
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # ---- roofline of the dominant kernel: the solve kernel, FP64 FMA pipe ----
+    fp64_peak = h.measure_fp64_peak()
+    iters_sum = float(info_np["iters"].astype(np.float64).sum())
+    solve_tflops = iters_sum * F_ITER / (solve_ms * 1e-3) / 1e12
+    step_ms = index_ms + knn_ms + solve_ms
+    kern = "ipm_quad_kernel" if BF >= 8192 else "ipm_solve_kernel"
+    traffic, traffic_src = ncu_traffic("ipm_quad" if BF >= 8192 else "ipm_solve")
+    hbm_peak, hbm_src = hbm_peak_gbs()
     b_knn = 12 * npts + N_H * (24 + K_NB * 12)
-    traffic = None  # dram bytes per launch of the index kernel, from the committed ncu --set full capture
-    try:
-        m = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r01.json")))["cloud_index"]["metrics"]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = sum(float(m[k]["value"]) * scale[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    except Exception:
-        pass
-    index_ms_avg = index_ms / max(rounds, 1)
-    knn_ms_avg = knn_ms / max(rounds, 1)
-    stage_ms = index_ms_avg + knn_ms_avg
-    achieved = B * b_knn / (index_ms_avg * 1e-3) / 1e9
-    denom = sum(single_step_ms)  # per-kernel times and shares come from the single-stream pass
-    roofline = {"kernel": "cloud_index_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
-                "traffic_note": "ncu dram__bytes_read+write of one launch at this workload (profiles/ncu_summary_r01.json); "
-                                "the reference's 16-byte pcl::PointXYZ records carry 4 padding bytes per point, so traffic "
-                                "= 16/12 x algorithmic + boxes",
-                "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": B * b_knn,
-                "as_laid_out_16B_GBps": B * 16 * npts / (index_ms_avg * 1e-3) / 1e9,
-                "avg_launch_ms": index_ms_avg, "step_share": index_ms / denom,
-                "measured": "CUDA events around the kernel on its stream, single-stream pass of this run (kernel runs alone)",
-                "avg_launch_ms_with_%d_batches_in_flight" % n_streams: ov["index"] / max(ov["n"], 1),
-                "knn_stage": {"what": "index build + box-pruned search (k-NN indices bit-exact)",
-                              "index_ms": index_ms_avg, "search_ms": knn_ms_avg,
-                              "achieved_GBps": B * b_knn / (stage_ms * 1e-3) / 1e9,
-                              "frac": B * b_knn / (stage_ms * 1e-3) / 1e9 / hbm_peak,
-                              "step_share": (index_ms + knn_ms) / denom}}
-    # ---- NLP kernel: FP64 work vs a DGEMM-measured FP64 peak on this box ----
-    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
-    for _ in range(2):
-        a @ a
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        a @ a
-    e1.record()
-    torch.cuda.synchronize()
-    fp64_peak = 5 * 2 * 4096 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
-    iters = info_np["iters"].astype(np.float64)
-    f_iter = (N_H - 1) * K_NB * 250 + N_H * 4275
-    solve_ms_avg = solve_ms / max(rounds, 1)
-    nlp_tflops = float(iters.sum()) * f_iter / (solve_ms_avg * 1e-3) / 1e12
-    roofline_nlp = {"kernel": "ipm_solve_kernel", "bound": "fp64 latency", "achieved": nlp_tflops, "peak": fp64_peak,
-                    "unit": "TFLOP/s", "frac": nlp_tflops / fp64_peak, "peak_source": "torch f64 matmul 4096^3 on this GPU",
-                    "flop_per_iter": f_iter, "avg_launch_ms": solve_ms_avg,
-                    "step_share": solve_ms / denom}
-
-    # ---- single-instance latency through the host API (cloud resident) ----
-    lat = []
-    for _ in range(30):
-        t0 = time.perf_counter()
-        h.round_host_ptrs(1, x0_h, ref_h, w_h, info_h, replan_h, speed=D.SPEED, safety_distance=D.SAFETY_DISTANCE)
-        lat.append((time.perf_counter() - t0) * 1e3)
-    lat = lat[5:]
+    idx_traffic, _ = ncu_traffic("cloud_index")
+    roofline = {
+        "kernel": kern, "bound": "fp64", "bound_note": "FP64 FMA pipe (neither hbm nor tensor: ~12 KB of HBM traffic per "
+        "instance, and tcgen05 has no FP64 path; the condensed DMMA variant was measured and rejected, DESIGN.md 4.3)",
+        "achieved": solve_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": solve_tflops / fp64_peak,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "peak_source": "hand-written dependent-FMA-chain kernel on this GPU, this run (ampc_measure_fp64_peak)",
+        "work_model": "sum of interior-point iterations x %d FP64 flop (SURVEY.md 8d: (N-1) K 250 + N 4275)" % F_ITER,
+        "iterations_per_launch": iters_sum, "avg_launch_ms": solve_ms, "step_share": solve_ms / step_ms,
+        "measured": "CUDA events around the kernel on its stream inside the timed region",
+        "cloud_index": {"kernel": "cloud_index_kernel", "bound": "hbm", "achieved": BF * b_knn / (index_ms * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "frac": BF * b_knn / (index_ms * 1e-3) / 1e9 / hbm_peak,
+                        "traffic": None if idx_traffic is None else idx_traffic * BF / 1024.0,
+                        "peak_source": hbm_src, "algorithmic_bytes_per_launch": BF * b_knn,
+                        "as_laid_out_16B_GBps": BF * 16 * npts / (index_ms * 1e-3) / 1e9,
+                        "avg_launch_ms": index_ms, "step_share": index_ms / step_ms},
+        "knn_stage": {"what": "index build + box-pruned search (k-NN indices bit-exact)", "index_ms": index_ms,
+                      "search_ms": knn_ms, "achieved_GBps": BF * b_knn / ((index_ms + knn_ms) * 1e-3) / 1e9,
+                      "frac": BF * b_knn / ((index_ms + knn_ms) * 1e-3) / 1e9 / hbm_peak,
+                      "step_share": (index_ms + knn_ms) / step_ms}}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(B, npts), "global_batch": world * B, "warm_start": args.warm,
-                   "tol": args.tol, "max_iter": args.max_iter, "parallelism": f"scene-sharded x{world}",
-                   "streams": n_streams, "streams_note": "independent batches in flight per GPU, each with its own frames",
-                   "l2": "inputs larger than L2 (%.0f MB of clouds per step per GPU)" % (B * npts * 16 / 1e6),
-                   "collective": "all_gather of per-instance costs (NCCL)" if world > 1 else "none"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "host_threads": len(e2e_lanes),
-                "note": "every step uploads all of its clouds and states from pinned host memory and reads all results back; "
-                        "PCIe-bound (clouds are 800 KB per instance)"},
+        "config": shared_config(args, world),
+        "run": {"batches_per_step": F, "instances_per_step_per_gpu": BF, "global_instances_per_step": world * BF,
+                "step": "one control round (index build + k-NN + solve) over %d batches of %d instances, each batch with "
+                        "its own %d-point scenes, submitted as one call; the solve kernel refills its warps from a "
+                        "queue over all of them" % (F, B, npts),
+                "timed_region_s": total_ms * 1e-3, "load_steps_before": n_load,
+                "parallelism": f"scene-sharded x{world}",
+                "l2": "inputs larger than L2 (%.1f GB of clouds per step per GPU)" % (BF * npts * 16 / 1e9),
+                "collective": "all_gather of per-instance costs (NCCL), every step" if world > 1 else "none"},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "roofline_nlp": roofline_nlp,
-        "single_stream": {"value": single_value, "unit": UNIT, "steps": n_single, "ms_per_step": single_ms / n_single,
-                          "note": "same steps, one batch in flight"},
-        "kernel_ms_overlapped": {"index": ov["index"] / max(ov["n"], 1), "knn_search": ov["knn"] / max(ov["n"], 1),
-                                 "solve": ov["solve"] / max(ov["n"], 1), "note": "%d batches in flight" % n_streams},
-        "latency": {"batch_step_ms_p50": statistics.median(single_step_ms), "batch_step_ms_p50_overlapped": statistics.median(step_ms), "single_instance_round_ms_p50": statistics.median(lat)},
-        "solver": {"converged_frac": float((info_np["status"] == 0).mean()),
-                   "status_counts": np.bincount(info_np["status"], minlength=4).tolist(),
-                   "iters_p50": float(np.median(iters)), "iters_p90": float(np.percentile(iters, 90)),
-                   "iters_max": int(iters.max()), "need_replan_frac": float(replan.float().mean().item())},
+        "stage_ms_per_step": {"index": index_ms, "knn_search": knn_ms, "solve": solve_ms},
+        "single_stream": single,
+        "solver": sstats,
     }
     if world == 1:
-        out["depth_path"] = depth_leg(A, torch, dev, local, hbm_peak, args, cpu=not args.no_cpu_baseline)
+        out["cold_start"] = cold_start_leg(A, torch, h, B, x0, ref, x0_np, ref_np, w, info, replan, stream)
+        out["reference_operating_point"] = truncated_leg(A, torch, h, B, x0, ref, w0, w, info, replan, stream, args)
+        out["depth_path"] = depth_resident_leg(A, torch, dev, local, args)
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         n = max(threads * 16, 128)
-        rates, kind, desc = cpu_reference(n, npts, threads, steps=2, warm=args.warm)
-        out["cpu_baseline"] = {"value": rates[-1], "unit": UNIT, "cores": threads, "kind": kind, "sample": desc}
+        rates, kind, desc, stage = cpu_reference(n, npts, threads, steps=2, warm=args.warm, tol=args.tol, max_iter=args.max_iter)
+        out["cpu_baseline"] = {"value": rates[-1], "unit": UNIT, "cores": threads, "kind": kind, "sample": desc,
+                               "stage_seconds_summed_over_threads": stage}
+        out["cpu_c0"] = cpu_c0(args, n_inst=60)
     else:
         out["cpu_baseline"] = None
     print(json.dumps(out), flush=True)
@@ -451,18 +413,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def depth_leg(A, torch, dev, local, hbm_peak, args, cpu=True, rows=200, cols=250, distinct=128):
-    """The step upstream of the clouds, reported next to the headline and not
-    part of it: (1) depth frames resident in HBM -> Obstacle + Edge clouds + tile indices
-    (ampc_depth_set_batch_dev), with the CPU restatement of FrameKDMap::ProcessDepth timed beside
-    it; (2) the control round measured end to end from HOST depth frames (what the reference's
-    AddVertex receives) instead of host clouds: 4 bytes per point over PCIe instead of 16."""
+def e2e_leg(A, torch, dist, dev, local, world, args, rows=200, cols=250, distinct=128, lanes_n=3):
+    """`e2e`: the same round through the host-buffer C-ABI, starting from what the reference's ingress
+    receives -- the depth frame (FrameKDMap::AddVertex, src/FrameKDMap.cpp:34-52): every step copies its
+    depth frames (f32 metres, 4 bytes per point) and states from pinned host memory, builds both clouds
+    and their indices on the device, runs k-NN + solve, and reads trajectories / costs / status back.
+    `lanes_n` host threads each drive their own handle, so one batch's upload overlaps the compute of
+    the others.  `cloud_upload` is the same with ready-made 16-byte clouds uploaded instead."""
     from concurrent.futures import ThreadPoolExecutor
     D, S = A.defaults, A.synth
     B = args.batch
+    rank = int(os.environ.get("RANK", "0"))
     cam = dict(fx=cols / 2, fy=cols / 2, cx=cols / 2, cy=rows / 2, resize_scale=1.0)
-    ids = [b % distinct for b in range(B)]
-    base = np.stack([S.forest_depth(s, rows, cols, sky=False) for s in range(distinct)])  # 50k-point clouds
+    ids = [rank * B + b for b in range(B)]
+    base = np.stack([S.forest_depth(rank * distinct + s, rows, cols, sky=False) for s in range(distinct)])
     depth_h = torch.from_numpy(base).repeat((B + distinct - 1) // distinct, 1, 1)[:B].contiguous().pin_memory()
     Twb = np.eye(4)
     Twb[2, 3] = D.HEIGHT
@@ -470,20 +434,146 @@ def depth_leg(A, torch, dev, local, hbm_peak, args, cpu=True, rows=200, cols=250
     x0_np, ref_np, _ = S.states_batch(ids, N_H, DT)
     w0_np = np.stack([S.warm_start(args.warm, x0_np[b], ref_np[b], N_H) for b in range(B)])
     x0_h, ref_h, w0_h = (torch.tensor(a).pin_memory() for a in (x0_np, ref_np, w0_np))
+    depth_np = depth_h.numpy()
 
-    def make():
-        hh = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=rows * cols, max_edge_points=rows * cols // 4,
-                      device=local)
+    def make(edge):
+        hh = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=rows * cols,
+                      max_edge_points=rows * cols // 4 if edge else 0, device=local)
         hh.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
         hh.set_camera(**cam)
         return dict(h=hh, w_h=torch.empty_like(w0_h).pin_memory(), info_h=torch.zeros((B, 48), dtype=torch.uint8).pin_memory(),
                     replan_h=torch.zeros(B, dtype=torch.int32).pin_memory())
 
-    lanes = [make(), make()]
-    hd = lanes[0]["h"]
-    # (1) resident
-    depth = depth_h.to(dev)
+    def run(step_fn, lanes, n):
+        with ThreadPoolExecutor(max_workers=len(lanes)) as ex:
+            list(ex.map(step_fn, [lanes[i % len(lanes)] for i in range(2 * len(lanes))]))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            list(ex.map(step_fn, [lanes[i % len(lanes)] for i in range(n)]))
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lanes = [make(True) for _ in range(lanes_n)]
+
+    def depth_step(ln):
+        ln["w_h"].copy_(w0_h)
+        ln["h"].depth_set_batch(depth_np, T_np)                       # H2D depth frames; clouds + indices on the device
+        ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
+                                safety_distance=D.SAFETY_DISTANCE)    # H2D states, k-NN, solve, D2H results
+
+    n = max(12, min(args.steps, 24))
+    dt = run(depth_step, lanes, n)
+    info = lanes[0]["info_h"].numpy().view(A.capi.INFO_DTYPE).reshape(B)
+    h2d = depth_h.numel() * 4 + T_np.nbytes + (x0_h.numel() + ref_h.numel() + w0_h.numel()) * 8
+    d2h = w0_h.numel() * 8 + B * 48 + B * 4
+    out = {"value": world * B * n / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": n, "host_threads": lanes_n, "instances_per_step": B,
+           "converged_frac": float((info["status"] == 0).mean()),
+           "ingress": "host depth frames %dx%d f32 (what FrameKDMap::AddVertex receives); Obstacle + Edge clouds and "
+                      "their indices are built on the device" % (rows, cols),
+           "h2d_GBps": h2d * n / dt / 1e9}
+    # the same with ready-made clouds uploaded (16 bytes per point): the number round 1 called e2e
+    clouds_h = torch.empty((B, rows * cols, 4), dtype=torch.float32).pin_memory()
+    clouds_h.copy_(S.forest_clouds_torch(ids, rows * cols, dev))
+    for ln in lanes:
+        ln["h"].cloud_set_layout(S.image_shape(rows * cols)[0])
+
+    def cloud_step(ln):
+        ln["w_h"].copy_(w0_h)
+        ln["h"].cloud_set_batch(clouds_h)
+        ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
+                                safety_distance=D.SAFETY_DISTANCE)
+
+    n2 = max(6, min(args.steps, 12))
+    dt2 = run(cloud_step, lanes, n2)
+    h2d2 = clouds_h.numel() * 4 + (x0_h.numel() + ref_h.numel() + w0_h.numel()) * 8
+    out["cloud_upload"] = {"value": world * B * n2 / dt2, "unit": UNIT, "h2d_bytes_per_step": h2d2,
+                           "d2h_bytes_per_step": d2h, "steps": n2, "h2d_GBps": h2d2 * n2 / dt2 / 1e9,
+                           "note": "ready-made 16-byte clouds uploaded every step instead of depth frames (PCIe-bound)"}
+    # what the host side alone can move: pinned H2D copy bandwidth of this process
+    buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    src = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        buf.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    out["pinned_h2d_GBps_alone"] = 4 * (256 << 20) / (time.perf_counter() - t0) / 1e9
+    for ln in lanes:
+        ln["h"].close()
+    return out
+
+
+def cold_start_leg(A, torch, h, B, x0, ref, x0_np, ref_np, w, info, replan, stream, steps=5):
+    """The reference's cold start (all-zero mNlpW0, src/HighLvlMpc.cpp:25-27) on one batch."""
+    D, S = A.defaults, A.synth
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):
+        if rep == 1:
+            e0.record()
+        for _ in range(steps):
+            w[:B].zero_()
+            h.cloud_index_dev(0, B, stream=stream)
+            h.round_dev(B, x0, ref, w, info_dev=info, replan_dev=replan, speed=D.SPEED, safety_distance=D.SAFETY_DISTANCE,
+                        stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    _, st = solver_stats(A, info[:B])
+    return {"warm_start": "cold", "value": B * steps / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
+            "ms_per_batch": e0.elapsed_time(e1) / steps, "solver": st, "note": "one 1024-instance batch in flight"}
+
+
+def truncated_leg(A, torch, h, B, x0, ref, w0, w, info, replan, stream, args):
+    """What a drop-in user sees with the reference's solver options (tol 1e-4, 10 iterations,
+    src/HighLvlMpc.cpp:19-20): distance of that iterate from this solver's converged optimum."""
+    D = A.defaults
+
+    def run(tol, mi):
+        h.set_solver_opts(tol=tol, max_iter=mi)
+        w[:B].copy_(w0[:B])
+        h.round_dev(B, x0, ref, w, info_dev=info, replan_dev=replan, speed=D.SPEED, safety_distance=D.SAFETY_DISTANCE,
+                    stream=stream)
+        torch.cuda.synchronize()
+        return w[:B].cpu().numpy().copy(), info[:B].cpu().numpy().view(A.capi.INFO_DTYPE).reshape(B).copy()
+
+    Wc, ic = run(args.tol, 200)
+    Wt, it = run(1e-4, 10)
+    h.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+    ok = ic["status"] == 0
+    gap = np.abs(Wt - Wc).max(axis=1)[ok]
+    u0 = np.abs(Wt[:, 10:14] - Wc[:, 10:14]).max(axis=1)[ok]
+    return {"options": {"tol": 1e-4, "max_iter": 10}, "instances": int(ok.sum()),
+            "stopped_by_tol_frac": float((it["status"][ok] == 0).mean()),
+            "linf_gap_to_converged": {"p50": float(np.median(gap)), "p90": float(np.percentile(gap, 90)), "max": float(gap.max()),
+                                      "frac_below_1e-4": float((gap < 1e-4).mean()), "frac_below_1e-2": float((gap < 1e-2).mean())},
+            "first_control_gap": {"p50": float(np.median(u0)), "p90": float(np.percentile(u0, 90)), "max": float(u0.max())},
+            "note": "l_inf over states and controls between the tol-1e-4 / 10-iteration iterate and the KKT<=1e-8 optimum "
+                    "of the same solver from the same warm start; u = w[10:14] is what the reference publishes"}
+
+
+def depth_resident_leg(A, torch, dev, local, args, rows=200, cols=250, distinct=128):
+    """The step upstream of the clouds: depth frames resident in HBM -> Obstacle +
+    Edge clouds + tile indices (ampc_depth_set_batch_dev), the numpy restatement timed beside it."""
+    D, S = A.defaults, A.synth
+    B = args.batch
+    hbm_peak, _ = hbm_peak_gbs()
+    cam = dict(fx=cols / 2, fy=cols / 2, cx=cols / 2, cy=rows / 2, resize_scale=1.0)
+    base = np.stack([S.forest_depth(s, rows, cols, sky=False) for s in range(distinct)])
+    depth = torch.from_numpy(base).repeat((B + distinct - 1) // distinct, 1, 1)[:B].contiguous().to(dev)
+    Twb = np.eye(4)
+    Twb[2, 3] = D.HEIGHT
+    T_np = np.ascontiguousarray(np.tile((Twb @ D.T_B_C).reshape(1, 16), (B, 1)))
     T = torch.from_numpy(T_np).to(dev)
+    hd = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=B, max_points=rows * cols, max_edge_points=rows * cols // 4, device=local)
+    hd.set_camera(**cam)
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3):
         hd.depth_set_batch_dev(depth, T, None, stream=st)
@@ -498,8 +588,6 @@ def depth_leg(A, torch, dev, local, hbm_peak, args, cpu=True, rows=200, cols=250
     ms = e0.elapsed_time(e1) / steps
     n_obst = float(np.mean([hd.cloud_count(s) for s in range(8)]))
     n_edge = float(np.mean([hd.cloud_count(s, A.capi.CLOUD_EDGE) for s in range(8)]))
-    # algorithmic bytes per frame: every source pixel once, the 16-byte records written, and the
-    # index pass reading them once
     b_frame = rows * cols * 4 + 2 * 16 * (n_obst + n_edge)
     out = {"what": "depth frame -> Obstacle + Edge cloud + tile index, frames resident in HBM",
            "workload": f"{B} frames {rows}x{cols} f32 ({distinct} distinct scenes), resize_scale 1",
@@ -508,31 +596,8 @@ def depth_leg(A, torch, dev, local, hbm_peak, args, cpu=True, rows=200, cols=250
            "gpu_launches_per_batch": (hd.launch_count() - l0) / steps,
            "achieved_GBps": B * b_frame / (ms * 1e-3) / 1e9,
            "frac_of_hbm_peak": B * b_frame / (ms * 1e-3) / 1e9 / hbm_peak}
-    del depth
-
-    # (2) end to end from host depth frames
-    def e2e_step(ln):
-        ln["w_h"].copy_(w0_h)
-        ln["h"].depth_set_batch(depth_h.numpy(), T_np)                # H2D depth frames, clouds + indices on the device
-        ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
-                                safety_distance=D.SAFETY_DISTANCE)    # H2D states, k-NN, solve, D2H results
-
-    n = 8
-    with ThreadPoolExecutor(max_workers=2) as ex:
-        list(ex.map(e2e_step, [lanes[i % 2] for i in range(4)]))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        list(ex.map(e2e_step, [lanes[i % 2] for i in range(n)]))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-    info = lanes[0]["info_h"].numpy().view(A.capi.INFO_DTYPE).reshape(B)
-    out["e2e_from_depth"] = {"value": B * n / dt, "unit": UNIT, "steps": n, "host_threads": 2,
-                             "h2d_bytes_per_step": depth_h.numel() * 4 + T_np.nbytes + (x0_h.numel() + ref_h.numel() + w0_h.numel()) * 8,
-                             "d2h_bytes_per_step": w0_h.numel() * 8 + B * 48 + B * 4,
-                             "converged_frac": float((info["status"] == 0).mean()),
-                             "note": "same round as e2e, but the host hands over the depth frames FrameKDMap::AddVertex receives "
-                                     "(f32 metres) and the clouds are built on the device"}
-    if cpu:
+    hd.close()
+    if not args.no_cpu_baseline:
         from oracle import depth_oracle as DO
         ocam = DO.Camera(**cam)
         Tm = T_np[0].reshape(4, 4)
@@ -541,18 +606,17 @@ def depth_leg(A, torch, dev, local, hbm_peak, args, cpu=True, rows=200, cols=250
             DO.process_depth(base[s], ocam, Tm, Tm)
         out["cpu_baseline"] = {"value": 8 / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "port",
                                "sample": "8 frames, numpy restatement of ProcessDepth + BuildEdgeCloud (no k-d tree build)"}
-    for ln in lanes:
-        ln["h"].close()
     return out
 
 
-def run_cpu_c0(args):
-    """BASELINE config C0 (the reference's own CPU-runnable case): single instance, N=20, K=8,
+def cpu_c0(args, n_inst=None):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): single instance, N=20, K=8,
     10 000-point cloud, ONE thread; p50/p90 of tree build, 20x8-NN, NLP solve and total."""
     import avoid_mpc_b200 as A
     from oracle import oracle as O
     D, S = A.defaults, A.synth
-    K, npts, n_inst = 8, 10000, max(50, args.steps * 50)
+    K, npts = 8, 10000
+    n_inst = n_inst or max(50, args.steps * 50)
     use_ref = O.ref_available()
     lb, ub = D.u_bounds()
     opts = O.default_opts()
@@ -575,35 +639,214 @@ def run_cpu_c0(args):
         iters.append(info.iters)
         conv += info.status == 0
     tot = [a + b + c_ for a, b, c_ in zip(t_build, t_knn, t_solve)]
-    q = lambda v, p_: float(np.percentile(np.array(v) * 1e3, p_))
-    print(json.dumps({"mode": "cpu_c0", "config": "single instance, N=20, K=8, 10000-pt cloud, 1 thread",
-                      "instances": n_inst, "knn_impl": "reference nanoflann (oracle/_ref)" if use_ref else "C restatement",
-                      "nlp_impl": "oracle interior-point port (tol 1e-8)", "unit": "ms",
-                      "tree_build": {"p50": q(t_build, 50), "p90": q(t_build, 90)},
-                      "knn_20x8": {"p50": q(t_knn, 50), "p90": q(t_knn, 90)},
-                      "nlp_solve": {"p50": q(t_solve, 50), "p90": q(t_solve, 90)},
-                      "total": {"p50": q(tot, 50), "p90": q(tot, 90)},
-                      "iters_p50": float(np.median(iters)), "converged_frac": conv / n_inst}), flush=True)
+    q = lambda v, p_: float(np.percentile(np.array(v) * 1e3, p_))  # noqa: E731
+    return {"mode": "cpu_c0", "config": "single instance, N=20, K=8, 10000-pt cloud, 1 thread",
+            "instances": n_inst, "knn_impl": "reference nanoflann (oracle/_ref)" if use_ref else "C restatement",
+            "nlp_impl": "oracle interior-point port (tol 1e-8)", "unit": "ms",
+            "tree_build": {"p50": q(t_build, 50), "p90": q(t_build, 90)},
+            "knn_20x8": {"p50": q(t_knn, 50), "p90": q(t_knn, 90)},
+            "nlp_solve": {"p50": q(t_solve, 50), "p90": q(t_solve, 90)},
+            "total": {"p50": q(tot, 50), "p90": q(tot, 90)},
+            "iters_p50": float(np.median(iters)), "converged_frac": conv / n_inst}
 
 
+# ------------------------------------------------------------------ configs[2] ----
+def run_best_of(args):
+    """BASELINE configs[2]: 4096 scenes x 32 Edge-tree initial guesses (131 072 NLP instances), best-cost
+    reduction, 1xB200.  One call: the 32 nearest Edge points of waypoint 0, N-1+G Obstacle queries per
+    scene (19 of the 20 queries are shared by a scene's guesses), 131 072 solves, best-of-32."""
+    torch, dist, world, rank, local, dev = dist_setup()
+    import avoid_mpc_b200 as A
+    D, S = A.defaults, A.synth
+    n_scenes, G, npts = args.scenes or 4096, args.guesses, args.npts
+    lo, hi = A.shard.scene_range(rank, world, n_scenes)
+    ns = hi - lo
+    ids = list(range(lo, hi))
+    stream = torch.cuda.current_stream().cuda_stream
+    h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=ns * G, max_scenes=ns, max_points=npts, max_edge_points=npts // 8, device=local)
+    h.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+    h.cloud_set_layout(S.image_shape(npts)[0])
+    fill_scenes(A, torch, h, ids, npts, dev)
+    # Edge clouds: pixels with a 4-neighbour depth jump > 0.5 m (SURVEY.md 8d); from the numpy generator of a
+    # few scenes per chunk would take minutes for 4096 scenes -- the edge set is recomputed on the device
+    W_img, H_img = S.image_shape(npts)
+    n_edge = []
+    for s0 in range(0, ns, 256):
+        c = S.forest_clouds_torch(ids[s0:s0 + 256], npts, dev)
+        rng = torch.linalg.norm(c[..., :3] - torch.tensor([D.T_B_C[0, 3], D.T_B_C[1, 3], D.HEIGHT + D.T_B_C[2, 3]],
+                                                         device=dev, dtype=torch.float32), dim=-1).view(-1, H_img, W_img)
+        jump = torch.zeros_like(rng, dtype=torch.bool)
+        jump[:, :, 1:] |= (rng[:, :, 1:] - rng[:, :, :-1]).abs() > 0.5
+        jump[:, :, :-1] |= (rng[:, :, 1:] - rng[:, :, :-1]).abs() > 0.5
+        jump[:, 1:, :] |= (rng[:, 1:, :] - rng[:, :-1, :]).abs() > 0.5
+        jump[:, :-1, :] |= (rng[:, 1:, :] - rng[:, :-1, :]).abs() > 0.5
+        jump = jump.view(-1, npts)
+        cap = npts // 8
+        e = torch.zeros((c.shape[0], cap, 4), dtype=torch.float32, device=dev)
+        cnt = np.zeros(c.shape[0], dtype=np.int32)
+        for i in range(c.shape[0]):
+            pts = c[i][jump[i]][:cap]
+            e[i, :pts.shape[0]] = pts
+            cnt[i] = pts.shape[0]
+        h.cloud_set_batch_dev(e, counts=cnt, first_scene=s0, kind=A.capi.CLOUD_EDGE, stream=stream)
+        torch.cuda.synchronize()
+        n_edge.extend(cnt.tolist())
+        del c, e
+    x0_np, ref_np, _ = S.states_batch(ids, N_H, DT)
+    # waypoint 0 sits next to an obstacle in the situations PlanWapionts acts on; keep the synthetic path
+    x0 = torch.tensor(x0_np, device=dev)
+    ref = torch.tensor(ref_np, device=dev)
+    w0_np = np.stack([S.warm_start(args.warm, x0_np[s], ref_np[s], N_H) for s in range(ns)])
+    w0 = torch.tensor(np.repeat(w0_np, G, axis=0), device=dev)
+    w = torch.empty_like(w0)
+    info = torch.zeros((ns * G, 48), dtype=torch.uint8, device=dev)
+    arg = torch.zeros(ns, dtype=torch.int32, device=dev)
+    best = torch.zeros(ns, dtype=torch.float64, device=dev)
+    gathered = torch.zeros(n_scenes, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        w.copy_(w0, non_blocking=True)
+        h.cloud_index_dev(0, ns, stream=stream)
+        h.cloud_index_dev(0, ns, kind=A.capi.CLOUD_EDGE, stream=stream)
+        h.guess_round_dev(ns, G, x0, ref, w, info_dev=info, argmin_dev=arg, best_dev=best, speed=D.SPEED, stream=stream)
+        if world > 1 and ns * world == n_scenes:
+            dist.all_gather_into_tensor(gathered, best)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    h.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(2, min(args.steps, 5))
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    prof = h.profile_get()
+    info_np, st = solver_stats(A, info)
+    warg, wbest = A.shard.best_of_scenes(info_np["cost"], info_np["status"], G)
+    a_np, b_np = arg.cpu().numpy(), best.cpu().numpy()
+    parity = bool((a_np == warg).all() and (b_np[warg >= 0] == wbest[warg >= 0]).all())
+    # how much the extra guesses buy: cost of the best guess relative to guess 0 (the reference's move)
+    c = info_np["cost"].reshape(ns, G)
+    gain = float(np.median((c[:, 0] - b_np) / np.maximum(1e-12, np.abs(c[:, 0]))))
+    if rank == 0:
+        print(json.dumps({"mode": "best_of", "metric": METRIC, "value": n_scenes * G / (ms * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "scenes": n_scenes, "guesses": G, "instances": n_scenes * G,
+                          "ms_per_step": ms, "scene_ticks_per_s": n_scenes / (ms * 1e-3),
+                          "stage_ms": {k: prof[k][0] / max(prof[k][1], 1) for k in ("index", "knn", "solve")},
+                          "obstacle_queries_per_scene": N_H - 1 + G, "edge_points_per_scene_mean": float(np.mean(n_edge)),
+                          "argmin_parity_vs_host_reduction": parity,
+                          "best_differs_from_guess0_frac": float((a_np != 0).mean()),
+                          "median_relative_cost_gain_over_guess0": gain, "solver": st,
+                          "config": {"workload": f"{n_scenes} scenes x {G} Edge-tree guesses, N={N_H}, K={K_NB}, {npts}-pt clouds",
+                                     "warm_start": args.warm, "tol": args.tol, "max_iter": args.max_iter}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ configs[3] ----
+def run_scenes65536(args):
+    """BASELINE configs[3]: 65 536 scenes sharded over the GPUs (8 192 per GPU on 8), one round each,
+    all-gather of the per-instance costs (512 KiB).  STRONG scaling: the job is the same at every N."""
+    torch, dist, world, rank, local, dev = dist_setup()
+    import avoid_mpc_b200 as A
+    D, S = A.defaults, A.synth
+    n_scenes, npts = args.scenes or 65536, args.npts
+    lo, hi = A.shard.scene_range(rank, world, n_scenes)
+    ns = hi - lo
+    chunk = min(ns, args.chunk)  # scenes resident at once per GPU (6.5 GB of clouds per 8192)
+    stream = torch.cuda.current_stream().cuda_stream
+    h = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=chunk, max_points=npts, device=local)
+    h.set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+    h.cloud_set_layout(S.image_shape(npts)[0])
+    n_chunks = (ns + chunk - 1) // chunk
+    # the clouds of every chunk stay resident (the job's input); chunks run back to back
+    handles = [h] + [None] * (n_chunks - 1)
+    data = []
+    for ci in range(n_chunks):
+        ids = list(range(lo + ci * chunk, min(hi, lo + (ci + 1) * chunk)))
+        if ci > 0:
+            handles[ci] = A.Handle(N=N_H, K=K_NB, dt=DT, max_batch=chunk, max_points=npts, device=local)
+            handles[ci].set_solver_opts(tol=args.tol, max_iter=args.max_iter)
+            handles[ci].cloud_set_layout(S.image_shape(npts)[0])
+        fill_scenes(A, torch, handles[ci], ids, npts, dev)
+        x0_np, ref_np, _ = S.states_batch(ids, N_H, DT)
+        w0_np = np.stack([S.warm_start(args.warm, x0_np[b], ref_np[b], N_H) for b in range(len(ids))])
+        data.append(dict(n=len(ids), x0=torch.tensor(x0_np, device=dev), ref=torch.tensor(ref_np, device=dev),
+                         w0=torch.tensor(w0_np, device=dev), w=torch.empty((len(ids), 10 + 14 * N_H), dtype=torch.float64, device=dev),
+                         info=torch.zeros((len(ids), 48), dtype=torch.uint8, device=dev)))
+    costs = torch.zeros(ns, dtype=torch.float64, device=dev)
+    even = ns * world == n_scenes
+    gathered = torch.zeros(n_scenes, dtype=torch.float64, device=dev) if world > 1 and even else None
+
+    def job():
+        o = 0
+        for hh, d in zip(handles, data):
+            d["w"].copy_(d["w0"], non_blocking=True)
+            hh.cloud_index_dev(0, d["n"], stream=stream)
+            hh.round_dev(d["n"], d["x0"], d["ref"], d["w"], info_dev=d["info"], speed=D.SPEED,
+                         safety_distance=D.SAFETY_DISTANCE, stream=stream)
+            costs[o:o + d["n"]].copy_(d["info"].view(torch.float64).view(d["n"], 6)[:, 0])
+            o += d["n"]
+        if gathered is not None:
+            dist.all_gather_into_tensor(gathered, costs)
+
+    job()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    steps = max(2, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        job()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    _, st = solver_stats(A, torch.cat([d["info"] for d in data]))
+    if rank == 0:
+        print(json.dumps({"mode": "scenes65536", "metric": METRIC, "value": n_scenes / (ms * 1e-3), "unit": UNIT,
+                          "n_gpus": world, "scenes": n_scenes, "scenes_per_gpu": ns, "chunk": chunk, "ms_per_job": ms,
+                          "scaling": "strong", "collective": "all_gather of %d costs (%d KiB)" % (n_scenes, n_scenes * 8 // 1024)
+                          if gathered is not None else "none", "solver_rank0": st,
+                          "config": {"workload": f"{n_scenes} scenes, N={N_H}, K={K_NB}, {npts}-pt clouds, one round each",
+                                     "warm_start": args.warm, "tol": args.tol, "max_iter": args.max_iter}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ configs[4] ----
 def run_knn_sweep(args):
-    """BASELINE config C4: k-NN only, cloud sizes 10k..1M points, Q=20, K=16, ~2 GB of clouds per
-    GPU; achieved GB/s of the k-NN stage (index build + search) against the measured HBM peak."""
-    import torch
+    """BASELINE configs[4]: k-NN only, cloud sizes 10k..1M points, Q=20, K=16, ~2 GB of clouds per GPU;
+    achieved GB/s of the k-NN stage (index build + search) against the measured HBM peak.  Under
+    torchrun every rank sweeps its own scenes; times are the max over ranks, bytes the sum."""
+    torch, dist, world, rank, local, dev = dist_setup()
     import avoid_mpc_b200 as A
     S = A.synth
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream().cuda_stream
-    try:
-        hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        hbm_peak = 6650.0
+    hbm_peak, _ = hbm_peak_gbs()
     rows, shuffled = [], []
+
+    def tmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for npts in (10000, 20000, 50000, 100000, 200000, 500000, 1000000):
         B = int(min(4096, max(8, 2e9 // (16 * npts))))
-        ids = list(range(B))
+        ids = list(range(rank * B, (rank + 1) * B))
         clouds = S.forest_clouds_torch(ids, npts, dev)
         _, ref, _ = S.states_batch(ids, N_H, DT)
         q = torch.tensor(np.ascontiguousarray(ref[:, :, :3]), device=dev)
@@ -616,6 +859,8 @@ def run_knn_sweep(args):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         ti, ts = [], []
         for it in range(3 + args.steps):
+            if world > 1:
+                dist.barrier()
             ev[0].record()
             h.cloud_index_dev(0, B, stream=stream)
             ev[1].record()
@@ -626,18 +871,19 @@ def run_knn_sweep(args):
                 ti.append(ev[0].elapsed_time(ev[1]))
                 ts.append(ev[1].elapsed_time(ev[2]))
         b_knn = 12 * npts + N_H * (24 + K_NB * 12)
-        t_i, t_s = statistics.median(ti), statistics.median(ts)
-        rows.append({"npts": npts, "batch": B, "index_ms": t_i, "search_ms": t_s,
-                     "index_GBps": B * b_knn / (t_i * 1e-3) / 1e9, "index_frac": B * b_knn / (t_i * 1e-3) / 1e9 / hbm_peak,
-                     "stage_GBps": B * b_knn / ((t_i + t_s) * 1e-3) / 1e9,
-                     "stage_frac": B * b_knn / ((t_i + t_s) * 1e-3) / 1e9 / hbm_peak,
-                     "as_laid_out_16B_index_GBps": B * 16 * npts / (t_i * 1e-3) / 1e9,
-                     "scene_rounds_per_s": B / ((t_i + t_s) * 1e-3)})
+        t_i, t_s = tmax(statistics.median(ti)), tmax(statistics.median(ts))
+        WB = world * B
+        rows.append({"npts": npts, "batch_per_gpu": B, "index_ms": t_i, "search_ms": t_s,
+                     "index_GBps": WB * b_knn / (t_i * 1e-3) / 1e9, "index_frac": WB * b_knn / (t_i * 1e-3) / 1e9 / (hbm_peak * world),
+                     "stage_GBps": WB * b_knn / ((t_i + t_s) * 1e-3) / 1e9,
+                     "stage_frac": WB * b_knn / ((t_i + t_s) * 1e-3) / 1e9 / (hbm_peak * world),
+                     "as_laid_out_16B_index_GBps": WB * 16 * npts / (t_i * 1e-3) / 1e9,
+                     "scene_rounds_per_s": WB / ((t_i + t_s) * 1e-3)})
         h.close()
         # the same points in arbitrary storage order (what KDTreeTwo::InitializeNew may be given):
-        # 64-consecutive-record tiles (AMPC_LAYOUT_UNORGANISED) against the Morton-bucketed copy
+        # 64-consecutive-record tiles (AMPC_LAYOUT_UNORGANISED) against the sorted copy
         # (AMPC_LAYOUT_SORT).  Both must return the very same indices.
-        if npts in (50000, 1000000):
+        if npts in (50000, 1000000) and world == 1:
             perm = torch.randperm(npts, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
             clouds = clouds[:, perm].contiguous()
             res = {}
@@ -667,8 +913,11 @@ def run_knn_sweep(args):
                                                             and (res["sort"][1] == res["unorganised"][1]).all().item())
         del clouds
         torch.cuda.empty_cache()
-    print(json.dumps({"mode": "knn_sweep", "unit": "GB/s", "peak": hbm_peak, "Q": N_H, "K": K_NB, "rows": rows,
-                      "shuffled_storage_order": shuffled}), flush=True)
+    if rank == 0:
+        print(json.dumps({"mode": "knn_sweep", "unit": "GB/s", "n_gpus": world, "peak_per_gpu": hbm_peak, "Q": N_H, "K": K_NB,
+                          "rows": rows, "shuffled_storage_order": shuffled}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -684,17 +933,23 @@ def main():
     ap.add_argument("--max-iter", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unorganised", action="store_true", help="do not pass the image row pitch to the index")
-    ap.add_argument("--mode", default="solves", choices=["solves", "knn_sweep", "cpu_c0"])
-    ap.add_argument("--streams", type=int, default=8, help="independent batches in flight per GPU")
-    ap.add_argument("--load-rounds", type=int, default=100,
-                    help="untimed rounds over all lanes before the measured passes (clock sampling window)")
+    ap.add_argument("--mode", default="solves", choices=["solves", "best_of", "scenes65536", "knn_sweep", "cpu_c0"])
+    ap.add_argument("--in-flight", type=int, default=32,
+                    help="batches of --batch instances per step (one call; each batch has its own scenes)")
+    ap.add_argument("--scenes", type=int, default=0, help="best_of / scenes65536: number of scenes (0 = the config's)")
+    ap.add_argument("--guesses", type=int, default=32)
+    ap.add_argument("--chunk", type=int, default=8192, help="scenes65536: scenes per call per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.mode == "knn_sweep":
         run_knn_sweep(args)
     elif args.mode == "cpu_c0":
-        run_cpu_c0(args)
+        print(json.dumps(cpu_c0(args)), flush=True)
+    elif args.mode == "best_of":
+        run_best_of(args)
+    elif args.mode == "scenes65536":
+        run_scenes65536(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:

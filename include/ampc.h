@@ -266,7 +266,29 @@ int ampc_best_of(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_i
 int ampc_best_of_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const ampc_solve_info *info_dev,
                      int32_t *argmin_dev, double *best_cost_dev, void *stream);
 
+/* ---- Edge-tree initial guesses + best-of-G in one call (BASELINE config C2): PlanWapionts
+ * (src/AvoidanceStateMachine.cpp:259-281) generalised from "the nearest Edge point" to the G
+ * nearest, every guess solved, the cheapest kept.  Per scene s (scene slot s: Obstacle + Edge
+ * cloud): guess g replaces waypoint 0 of ref_s by the g-th nearest Edge point of it (g = 0 is the
+ * reference's move; a guess beyond the number of Edge points leaves the waypoint in place).
+ * Instances are laid out scene-major, b = s*G + g.  Only stage 0's neighbours differ between the
+ * guesses of a scene, so the Obstacle cloud is queried at N-1+G sites per scene, not N*G.
+ *   x0[n_scenes*10], ref[n_scenes*N*10], pos_x[n_scenes] (NULL: x0[0]), speed: as ampc_round_batch
+ *   w_inout[n_scenes*G*n_w]  warm start in / solutions out, info[n_scenes*G]
+ *   argmin[n_scenes], best_cost[n_scenes]: as ampc_best_of (both NULL: skipped).  G <= 32. */
+int ampc_guess_round_batch(ampc_handle *h, int32_t n_scenes, int32_t G, const double *x0, const double *ref,
+                           const double *pos_x, double speed, double *w_inout, ampc_solve_info *info_out,
+                           int32_t *argmin_out, double *best_cost_out);
+int ampc_guess_round_batch_dev(ampc_handle *h, int32_t n_scenes, int32_t G, const double *x0_dev,
+                               const double *ref_dev, const double *pos_x_dev, double speed,
+                               double *w_inout_dev, ampc_solve_info *info_dev, int32_t *argmin_dev,
+                               double *best_cost_dev, void *stream);
+
 /* ---- instrumentation ---------------------------------------------------- */
+/* FP64 FMA throughput of the handle's device in TFLOP/s, measured with a hand-written kernel of
+ * independent dependent-FMA chains (2 flop per FMA): the denominator of the solve kernels'
+ * roofline fraction.  Synchronises. */
+int ampc_measure_fp64_peak(ampc_handle *h, double *tflops_out);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 int64_t ampc_launch_count(const ampc_handle *h);
 /* per-stage device time from CUDA events recorded on the caller's stream around

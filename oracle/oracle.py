@@ -29,7 +29,7 @@ def build(force: bool = False) -> None:
     ):
         subprocess.run(["make", "-C", _HERE, "liboracle.so"], check=True, capture_output=True)
     if os.path.exists("/root/reference/roswrapper/ros/src/avoid_mpc/include/kd_tree_two.h") and (
-        force or not os.path.exists(_REF)
+        force or not os.path.exists(_REF) or not os.path.exists(os.path.join(_HERE, "_ref", "libampc_cpu_arm.so"))
     ):
         subprocess.run(["make", "-C", _HERE, "ref"], check=True, capture_output=True)
 
@@ -220,6 +220,43 @@ class RefTree:
         if getattr(self, "h", None):
             ref_lib().ref_tree_destroy(self.h)
             self.h = None
+
+
+# ------------------------------------------------- native multi-threaded CPU arm ----
+_ARM = os.path.join(_HERE, "_ref", "libampc_cpu_arm.so")
+_arm = None
+
+
+def cpu_arm_available() -> bool:
+    build()
+    return os.path.exists(_ARM)
+
+
+def cpu_arm_run(n, threads, clouds16, x0, ref, tgt, tail34, W0, N, K, dt, lbu, ubu, opts: "Opts | None" = None):
+    """n control rounds (reference kd-tree build + N x K-NN + packing + oracle NLP solve) on `threads`
+    std::threads (oracle/cpu_arm.cpp).  clouds16: (n_distinct, npts, 4) f32; x0/ref/tgt/W0 per distinct
+    scene.  Returns (wall seconds, status[n], iters[n], stage seconds [build, knn, solve] summed)."""
+    global _arm
+    if _arm is None:
+        A = C.CDLL(_ARM)
+        A.cpu_arm_run.restype = C.c_double
+        A.cpu_arm_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _dp, _dp, _dp, _dp, _dp, C.c_int, C.c_int,
+                                  C.c_double, _dp, _dp, C.POINTER(Opts), _ip, _ip, _dp]
+        _arm = A
+    clouds16 = np.ascontiguousarray(clouds16, dtype=np.float32)
+    nd, npts = clouds16.shape[0], clouds16.shape[1]
+    x0, ref, tgt, W0 = (np.ascontiguousarray(a, dtype=np.float64) for a in (x0, ref, tgt, W0))
+    tail34 = np.ascontiguousarray(tail34, dtype=np.float64)
+    assert tail34.size == 34 and clouds16.shape[2] == 4
+    lbu = np.ascontiguousarray(lbu, dtype=np.float64)
+    ubu = np.ascontiguousarray(ubu, dtype=np.float64)
+    opts = opts or default_opts()
+    st = np.zeros(n, dtype=np.int32)
+    it = np.zeros(n, dtype=np.int32)
+    stage = np.zeros(3)
+    wall = _arm.cpu_arm_run(n, threads, nd, npts, clouds16.ctypes.data, _d(x0), _d(ref), _d(tgt), _d(tail34), _d(W0),
+                            N, K, dt, _d(lbu), _d(ubu), C.byref(opts), _i(st), _i(it), _d(stage))
+    return wall, st, it, stage
 
 
 # ------------------------------------------------------------------ NLP ----

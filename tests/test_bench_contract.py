@@ -26,6 +26,12 @@ def test_reference_arm_line():
     assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 3
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms print the same config dict, key for key (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    ns = argparse.Namespace(batch=1024, npts=10000, warm="ref", tol=1e-8, max_iter=50)
+    assert d["config"] == bench.shared_config(ns, 1)
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]

@@ -144,6 +144,11 @@ def test_edge_guesses_best_of():
     arg, best = h.best_of(info, n_scenes, G)
     warg, wbest = A.shard.best_of_scenes(info["cost"], info["status"], G)
     assert (arg == warg).all() and (best == wbest).all()
+    # the one-call form with shared queries (N-1+G Obstacle queries per scene instead of N*G)
+    # must give the very same instances, bit for bit
+    W2, info2, arg2, best2 = h.guess_round(np.stack(x0s), np.stack(refs), W0, G)
+    assert (W2 == W).all() and (info2["cost"] == info["cost"]).all() and (info2["iters"] == info["iters"]).all()
+    assert (arg2 == arg).all() and (best2 == best).all()
     # the winning instance of each scene against the oracle
     lb, ub = D.u_bounds()
     for s in range(n_scenes):
