@@ -83,7 +83,8 @@ struct ampc_handle {
     int64_t launches = 0;
     std::string err;
     // quad solve kernel: workspace of the resident warps, refill counter, tuning knobs
-    DevBuf quad_ws, quad_counter;
+    DevBuf quad_ws, quad_counter, quad_order_buf;
+    bool quad_order = true; // AMPC_QUAD_ORDER=0: take the instances in index order
     int n_sm = 148;
     int smem_per_sm = 228 * 1024;
     int quad_warps_per_sm = 8; // AMPC_QUAD_WARPS_PER_SM (255 registers per thread allow 8)
@@ -641,15 +642,28 @@ int launch_solve_quad(ampc_handle *h, int B, const double *prefix_dev, double *w
         }
         CK(h->quad_ws.reserve(full > need ? full : need));
     }
-    CK(h->quad_counter.reserve(256));
-    CK(cudaMemsetAsync(h->quad_counter.p, 0, 4, st));
+    // counter[0]: queue head; counter[1..64]: class histogram + running offsets of the ordering
+    CK(h->quad_counter.reserve(512));
+    CK(cudaMemsetAsync(h->quad_counter.p, 0, 512, st));
     double *wsp = h->quad_ws.as<double>();
     int32_t *cnt = h->quad_counter.as<int32_t>();
+    const int32_t *order = nullptr;
+    if (h->quad_order && B > warps * Q && h->cfg.K > 0 && h->cfg.N > 1) {
+        // more instances than slots: the queue is refilled, take the hard instances first
+        CK(h->quad_order_buf.reserve((size_t)B * 8));
+        int32_t *cls = h->quad_order_buf.as<int32_t>(), *ord = cls + B;
+        solve_order_class_kernel<<<(B + 7) / 8, 256, 0, st>>>(B, h->cfg.N, h->cfg.K, h->n_prefix, h->radius, prefix_dev,
+                                                           active, cls, cnt + 1);
+        solve_order_scatter_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, cls, cnt + 1, ord);
+        h->launches += 2;
+        CK(cudaGetLastError());
+        order = ord;
+    }
     switch (qs) {
-    case 0: ipm_quad_kernel<0><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
-    case 1: ipm_quad_kernel<1><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
-    case 2: ipm_quad_kernel<2><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
-    default: ipm_quad_kernel<3><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, wsp, cnt); break;
+    case 0: ipm_quad_kernel<0><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    case 1: ipm_quad_kernel<1><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    case 2: ipm_quad_kernel<2><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    default: ipm_quad_kernel<3><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -753,6 +767,8 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
     }
     if (const char *e = std::getenv("AMPC_SOLVE_KERNEL"))
         h->solve_kernel = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "quad") == 0 ? 2 : 0);
+    if (const char *e = std::getenv("AMPC_QUAD_ORDER"))
+        h->quad_order = std::atoi(e) != 0;
     if (const char *e = std::getenv("AMPC_QUAD_MIN_BATCH")) {
         const int v = std::atoi(e);
         if (v >= 1) h->quad_min_batch = v;
@@ -841,7 +857,7 @@ void ampc_destroy(ampc_handle *h) {
                      &h->depth_scratch, &h->depth_flag, &h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
-                     &h->ws_i, &h->ws_counter, &h->quad_ws, &h->quad_counter, &h->gs_sites, &h->gs_nb, &h->gs_epts, &h->gs_ecnt, &h->gs_q0, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
+                     &h->ws_i, &h->ws_counter, &h->quad_ws, &h->quad_counter, &h->quad_order_buf, &h->gs_sites, &h->gs_nb, &h->gs_epts, &h->gs_ecnt, &h->gs_q0, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,
                      &h->tk_c1, &h->tk_ep, &h->tk_ec, &h->tk_ed, &h->tk_safe, &h->tk_rounds};
     for (DevBuf *b : all)
         b->release();
