@@ -61,7 +61,9 @@ struct ampc_handle {
     int n_w = 0, n_prefix = 0;
     cudaStream_t stream = nullptr;
     // clouds: [kind] slot buffers + counts
-    DevBuf cloud[2], counts[2], boxes[2], nan_flags[2];
+    DevBuf cloud[2], counts[2], boxes[2], gboxes[2], nan_flags[2];
+    int slot_groups[2] = {0, 0};
+    bool knn_two_level = true; // AMPC_KNN_TWO_LEVEL=0: the one-level search of round 1
     DevBuf sorted[2]; // Morton-bucketed copies for layout -1 (allocated on first use)
     bool sort_smem_set = false;
     int slot_points[2] = {0, 0};
@@ -478,7 +480,7 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     const int64_t warps = (int64_t)B * Q;
     const int target_warps = 148 * 16;
     if (warps < target_warps) {
-        const int max_useful = (h->slot_points[kind] / KT_TILE + 63) / 64; // >= 64 tiles per segment
+        const int max_useful = (h->slot_points[kind] / KT_TILE + 63) / 64; // >= 64 tiles (4 groups) per segment
         segs = (int)((target_warps + warps - 1) / warps);
         if (segs > max_useful) segs = max_useful;
         if (segs > 64) segs = 64;
@@ -488,6 +490,8 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     P.clouds = h->cloud[kind].as<float4>();
     P.sorted = h->sorted[kind].as<float4>();
     P.boxes = h->boxes[kind].as<float4>();
+    P.gboxes = h->gboxes[kind].as<float4>();
+    P.slot_groups = h->slot_groups[kind];
     P.counts = h->counts[kind].as<int32_t>();
     P.slot_points = h->slot_points[kind];
     P.slot_tiles = h->slot_tiles[kind];
@@ -514,7 +518,10 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     const dim3 grid(B, (Q + KS_WARPS - 1) / KS_WARPS, segs);
     if (grid.y > 65535u)
         return fail(h, AMPC_ERR_UNSUPPORTED, "too many queries per instance");
-    knn_search_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
+    if (h->knn_two_level)
+        knn_search2_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
+    else
+        knn_search_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
     h->launches++;
     CK(cudaGetLastError());
     if (segs > 1) {
@@ -572,6 +579,12 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
         h->launches++;
         CK(cudaGetLastError());
     }
+    // second level: boxes of the groups of 16 tiles
+    group_boxes_kernel<<<dim3(n_scenes, (h->slot_groups[kind] + 7) / 8), 256, 0, st>>>(
+        h->boxes[kind].as<float4>(), h->gboxes[kind].as<float4>(), h->counts[kind].as<int32_t>(), h->slot_tiles[kind],
+        h->slot_groups[kind], h->layout[kind].as<int32_t>(), first_scene);
+    h->launches++;
+    CK(cudaGetLastError());
     return prof_end(h, slot, st);
 }
 
@@ -767,6 +780,8 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
     }
     if (const char *e = std::getenv("AMPC_SOLVE_KERNEL"))
         h->solve_kernel = std::strcmp(e, "warp") == 0 ? 1 : (std::strcmp(e, "quad") == 0 ? 2 : 0);
+    if (const char *e = std::getenv("AMPC_KNN_TWO_LEVEL"))
+        h->knn_two_level = std::atoi(e) != 0;
     if (const char *e = std::getenv("AMPC_QUAD_ORDER"))
         h->quad_order = std::atoi(e) != 0;
     if (const char *e = std::getenv("AMPC_QUAD_MIN_BATCH")) {
@@ -822,6 +837,9 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
         h->slot_tiles[kind] = (int)tile_capacity(h->slot_points[kind]);
         if ((e = h->boxes[kind].reserve((size_t)cfg->max_scenes * h->slot_tiles[kind] * 32)) != cudaSuccess)
             return bail(e, "cudaMalloc(tile boxes)");
+        h->slot_groups[kind] = (int)group_capacity(h->slot_tiles[kind]);
+        if ((e = h->gboxes[kind].reserve((size_t)cfg->max_scenes * h->slot_groups[kind] * 32)) != cudaSuccess)
+            return bail(e, "cudaMalloc(group boxes)");
         if ((e = cudaMemset(h->counts[kind].p, 0, (size_t)cfg->max_scenes * 4)) != cudaSuccess)
             return bail(e, "cudaMemset(counts)");
         if ((e = h->nan_flags[kind].reserve((size_t)cfg->max_scenes * 4)) != cudaSuccess)
@@ -854,7 +872,7 @@ void ampc_destroy(ampc_handle *h) {
     if (h->stream)
         cudaStreamSynchronize(h->stream);
     DevBuf *all[] = {&h->sorted[0], &h->sorted[1], &h->layout[0], &h->layout[1], &h->depth_stage, &h->depth_T, &h->depth_tab,
-                     &h->depth_scratch, &h->depth_flag, &h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
+                     &h->depth_scratch, &h->depth_flag, &h->cloud[0], &h->cloud[1], &h->counts[0], &h->counts[1], &h->boxes[0], &h->boxes[1], &h->gboxes[0], &h->gboxes[1], &h->nan_flags[0], &h->nan_flags[1], &h->raw_stage,
                      &h->queries, &h->prefix, &h->w, &h->info, &h->knn_idx, &h->knn_d2, &h->knn_cnt,
                      &h->knn_pts, &h->scene_of, &h->x0, &h->ref, &h->posx, &h->replan, &h->ws_d,
                      &h->ws_i, &h->ws_counter, &h->quad_ws, &h->quad_counter, &h->quad_order_buf, &h->gs_sites, &h->gs_nb, &h->gs_epts, &h->gs_ecnt, &h->gs_q0, &h->bo_arg, &h->bo_cost, &h->tk_active, &h->tk_q0, &h->tk_d1,

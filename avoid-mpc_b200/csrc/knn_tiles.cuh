@@ -97,10 +97,45 @@ __host__ __device__ inline int tile_layout(int n, int hint, int64_t slot_tiles) 
     return hint;
 }
 
+// ---- second level of the index: groups of 16 tiles (a 4x4 block of 8x8 image patches = 32x32
+// pixels of an organised cloud; 16 consecutive tiles = 1024 consecutive records otherwise), one
+// 32-byte box record each.  The search tests the groups first and only looks at the tiles of the
+// groups that can still hold a neighbour.
+constexpr int KG_TILES = 16;
+struct GroupGeom {
+    int org, tiles_x, tiles_y, groups_x, n_groups, n_tiles;
+    __host__ __device__ explicit GroupGeom(const TileGeom &g) {
+        n_tiles = g.n_tiles;
+        if (g.row_w > 0) {
+            org = 1, tiles_x = g.tiles_x, tiles_y = g.tiles_x > 0 ? g.n_tiles / g.tiles_x : 0;
+            groups_x = (tiles_x + 3) / 4;
+            n_groups = groups_x * ((tiles_y + 3) / 4);
+        } else {
+            org = 0, tiles_x = tiles_y = groups_x = 0;
+            n_groups = (n_tiles + KG_TILES - 1) / KG_TILES;
+        }
+    }
+    // tile s (0..15) of group g, or -1; (ty, tx) = its patch coordinates in an organised cloud
+    __device__ int tile(int g, int s, int &ty, int &tx) const {
+        if (org) {
+            const int gy = g / groups_x, gx = g - gy * groups_x;
+            ty = 4 * gy + (s >> 2), tx = 4 * gx + (s & 3);
+            return (ty < tiles_y && tx < tiles_x) ? ty * tiles_x + tx : -1;
+        }
+        ty = tx = 0;
+        const int t = KG_TILES * g + s;
+        return t < n_tiles ? t : -1;
+    }
+};
+// group slots per scene (an organised cloud one tile row high has ceil(tiles/4) groups)
+__host__ __device__ inline int64_t group_capacity(int64_t slot_tiles) { return slot_tiles / 4 + 64; }
+
 struct KnnParams {
     const float4 *clouds;    // slot s at clouds + s*slot_points
     const float4 *sorted;    // Morton-bucketed copies (x, y, z, original index) of the scenes whose layout is -1
     const float4 *boxes;     // slot s at boxes + s*slot_tiles*2 (two float4 per tile)
+    const float4 *gboxes;    // slot s at gboxes + s*slot_groups*2 (two float4 per group of tiles)
+    int64_t slot_groups;
     const int32_t *counts;   // points held in each slot (after the NaN filter)
     int64_t slot_points;
     int64_t slot_tiles;
@@ -843,6 +878,255 @@ knn_search_kernel(const KnnParams P) {
                     scan_tile(tsrc, n, g, c0 + jj, qx, qy, qz, e, kth, k, lane, by_w);
                     bound = fmin(bound, kth);
                 }
+            }
+        }
+        __syncwarp();
+    }
+    if (P.segs == 1) {
+        knn_write_result(P, cloud, n, b, q, e, lane);
+    } else if (lane < k) {
+        const int64_t o = ((((int64_t)b * P.Q + q) * P.segs) + seg) * k + lane;
+        P.ws_d[o] = e.d;
+        P.ws_i[o] = e.i;
+    }
+}
+
+// ---- group boxes: one warp per group reduces the boxes of its (up to) 16 tiles ------------
+__global__ void __launch_bounds__(256)
+group_boxes_kernel(const float4 *__restrict__ boxes, float4 *__restrict__ gboxes, const int32_t *__restrict__ counts,
+                   int64_t slot_tiles, int64_t slot_groups, const int32_t *__restrict__ layout, int first_scene) {
+    const int scene = first_scene + blockIdx.x;
+    const int lane = threadIdx.x & 31, g = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int n = counts[scene];
+    const TileGeom tg(n, tile_layout(n, layout[scene], slot_tiles));
+    const GroupGeom gg(tg);
+    if (g >= gg.n_groups)
+        return;
+    const float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
+    int ty, tx;
+    const int t = lane < KG_TILES ? gg.tile(g, lane, ty, tx) : -1;
+    float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+    int cnt = 0;
+    if (t >= 0) {
+        const float4 a = bx[2 * (int64_t)t], h = bx[2 * (int64_t)t + 1];
+        lx = a.x, ly = a.y, lz = a.z, hx = a.w, hy = h.x, hz = h.y, cnt = __float_as_int(h.z);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        lx = fminf(lx, __shfl_xor_sync(AMPC_FULL_MASK, lx, o));
+        ly = fminf(ly, __shfl_xor_sync(AMPC_FULL_MASK, ly, o));
+        lz = fminf(lz, __shfl_xor_sync(AMPC_FULL_MASK, lz, o));
+        hx = fmaxf(hx, __shfl_xor_sync(AMPC_FULL_MASK, hx, o));
+        hy = fmaxf(hy, __shfl_xor_sync(AMPC_FULL_MASK, hy, o));
+        hz = fmaxf(hz, __shfl_xor_sync(AMPC_FULL_MASK, hz, o));
+        cnt += __shfl_xor_sync(AMPC_FULL_MASK, cnt, o);
+    }
+    if (lane == 0) {
+        float4 *dst = gboxes + ((int64_t)scene * slot_groups + g) * 2;
+        dst[0] = make_float4(lx, ly, lz, hx);
+        dst[1] = make_float4(hy, hz, __int_as_float(cnt), 0.f);
+    }
+}
+
+// the (up to) 64 points of a tile, two per lane, loaded but not yet used
+struct TileLoad {
+    float4 p0, p1;
+    int i0, i1;
+};
+__device__ __forceinline__ TileLoad load_tile(const float4 *cloud, int n, const TileGeom &g, int tile, int ty, int tx,
+                                              int lane) {
+    TileLoad L;
+    if (g.row_w > 0) { // patch coordinates known: no division
+        const int col = 8 * tx + (lane & 7);
+        const int a = (8 * ty + (lane >> 3)) * g.row_w + col, b = a + 4 * g.row_w;
+        const bool ok = col < g.row_w;
+        L.i0 = ok && a < n ? a : -1;
+        L.i1 = ok && b < n ? b : -1;
+    } else {
+        const int a = tile * KT_TILE + lane, b = a + 32;
+        L.i0 = a < n ? a : -1;
+        L.i1 = b < n ? b : -1;
+    }
+    L.p0 = L.p1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (L.i0 >= 0) L.p0 = knn_ldg(cloud + L.i0);
+    if (L.i1 >= 0) L.p1 = knn_ldg(cloud + L.i1);
+    return L;
+}
+// exact distances of a loaded tile's points, candidates into the list (as scan_tile)
+__device__ __forceinline__ void consume_tile(const TileLoad &L, double qx, double qy, double qz, TopK &e, double &kth,
+                                             int k, int lane, bool by_w) {
+    double d0 = INFINITY, d1 = INFINITY;
+    uint32_t id0 = (uint32_t)L.i0, id1 = (uint32_t)L.i1;
+    if (L.i0 >= 0) {
+        d0 = knn_dist2(qx, qy, qz, L.p0.x, L.p0.y, L.p0.z);
+        if (by_w) id0 = (uint32_t)__float_as_int(L.p0.w);
+    }
+    if (L.i1 >= 0) {
+        d1 = knn_dist2(qx, qy, qz, L.p1.x, L.p1.y, L.p1.z);
+        if (by_w) id1 = (uint32_t)__float_as_int(L.p1.w);
+    }
+    const bool c0 = L.i0 >= 0 && d0 <= kth, c1 = L.i1 >= 0 && d1 <= kth;
+    unsigned m0 = __ballot_sync(AMPC_FULL_MASK, c0);
+    unsigned m1 = __ballot_sync(AMPC_FULL_MASK, c1);
+    if (k <= 16 && __popc(m0) + __popc(m1) >= KS_DENSE) {
+        merge_dense_tile(e, k, c0 ? d0 : INFINITY, c0 ? id0 : 0xffffffffu, c1 ? d1 : INFINITY,
+                         c1 ? id1 : 0xffffffffu, lane);
+        kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        return;
+    }
+    while (m0) {
+        const int src = __ffs(m0) - 1;
+        m0 &= m0 - 1;
+        const double d = __shfl_sync(AMPC_FULL_MASK, d0, src);
+        if (d <= kth) {
+            topk_insert(e, k, d, __shfl_sync(AMPC_FULL_MASK, id0, src), lane);
+            kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        }
+    }
+    while (m1) {
+        const int src = __ffs(m1) - 1;
+        m1 &= m1 - 1;
+        const double d = __shfl_sync(AMPC_FULL_MASK, d1, src);
+        if (d <= kth) {
+            topk_insert(e, k, d, __shfl_sync(AMPC_FULL_MASK, id1, src), lane);
+            kth = fmin(kth, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        }
+    }
+}
+
+// One group: lower bounds of its tiles (lanes 0..15), the tiles that can still hold a neighbour
+// visited nearest-bound first; the points of the next tile are in flight while the current one
+// is merged.  `bound` as in the kernel below.
+__device__ __forceinline__ void visit_group(const KnnParams &P, const float4 *boxes, const float4 *tsrc, int n,
+                                            const TileGeom &g, const GroupGeom &gg, int G, const QueryF &qf, double qx,
+                                            double qy, double qz, TopK &e, double &bound, int k, int lane, bool by_w) {
+    int ty, tx;
+    const int t = lane < KG_TILES ? gg.tile(G, lane, ty, tx) : -1;
+    float lb = INFINITY;
+    double ub = INFINITY;
+    if (t >= 0) {
+        const float4 a = knn_ldg(boxes + 2 * (int64_t)t), h = knn_ldg(boxes + 2 * (int64_t)t + 1);
+        lb = knn_box_lb32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
+        if (__float_as_int(h.z) >= k) // the tile alone holds >= k points within its farthest corner
+            ub = (double)knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
+    }
+    bound = fmin(bound, warp_min(ub));
+    // lanes with a tile still to visit; an empty tile (lb = +inf) never is -- `bound` itself is
+    // +inf while fewer than k points have been seen, so "lb <= bound" alone would not end
+    bool live = t >= 0 && lb < INFINITY;
+    if (!live) lb = INFINITY;
+    auto argmin = [&](float &best, int &bl) {
+        best = lb, bl = lane;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) { // lanes 16..31 hold +inf
+            const float ob = __shfl_xor_sync(AMPC_FULL_MASK, best, o);
+            const int ol = __shfl_xor_sync(AMPC_FULL_MASK, bl, o);
+            if (ob < best || (ob == best && ol < bl)) best = ob, bl = ol;
+        }
+        best = __shfl_sync(AMPC_FULL_MASK, best, 0);
+        bl = __shfl_sync(AMPC_FULL_MASK, bl, 0);
+    };
+    float best;
+    int bl;
+    if (!__any_sync(AMPC_FULL_MASK, live))
+        return;
+    argmin(best, bl);
+    if (!((double)best <= bound))
+        return;
+    TileLoad A = load_tile(tsrc, n, g, __shfl_sync(AMPC_FULL_MASK, t, bl), __shfl_sync(AMPC_FULL_MASK, ty, bl),
+                           __shfl_sync(AMPC_FULL_MASK, tx, bl), lane);
+    if (lane == bl) lb = INFINITY, live = false;
+    for (;;) {
+        const bool any_live = __any_sync(AMPC_FULL_MASK, live);
+        argmin(best, bl);
+        const bool more = any_live && (double)best <= bound;
+        TileLoad B = A;
+        if (more)
+            B = load_tile(tsrc, n, g, __shfl_sync(AMPC_FULL_MASK, t, bl), __shfl_sync(AMPC_FULL_MASK, ty, bl),
+                          __shfl_sync(AMPC_FULL_MASK, tx, bl), lane);
+        double kth = fmin(bound, __shfl_sync(AMPC_FULL_MASK, e.d, k - 1));
+        consume_tile(A, qx, qy, qz, e, kth, k, lane, by_w);
+        bound = fmin(bound, kth);
+        if (!more || !((double)best <= bound))
+            break; // every remaining tile of the group has a bound at least `best`
+        if (lane == bl) lb = INFINITY, live = false;
+        A = B;
+    }
+}
+
+// ---- exact k-NN, two-level: one warp per (instance, query).  Group lower bounds first (a 50k-
+// point cloud has ~56 groups against 782 tiles), two best-first group picks to tighten the
+// bound, then one sweep over the groups in storage order.  `bound`: no point farther than this
+// can be among the k nearest = min of the list's k-th entry and of the farthest-corner distance of
+// any group or tile seen that holds at least k points.
+constexpr int KS_GCHUNK = 1024; // group lower bounds kept in shared memory per warp (16384 tiles = 1M points)
+constexpr int KS_GPICKS = 2;
+__global__ void __launch_bounds__(KS_WARPS * 32, 6)
+knn_search2_kernel(const KnnParams P) {
+    __shared__ float sGLB[KS_WARPS][KS_GCHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = blockIdx.y * KS_WARPS + warp, b = blockIdx.x, seg = blockIdx.z;
+    if (q >= P.Q || (P.active && P.active[b] == 0))
+        return;
+    const int k = P.k;
+    const int scene = P.scene_of ? P.scene_of[b] : b;
+    const int n = P.counts[scene];
+    const float4 *cloud = P.clouds + (int64_t)scene * P.slot_points;
+    const float4 *boxes = P.boxes + (int64_t)scene * P.slot_tiles * 2;
+    const float4 *gboxes = P.gboxes + (int64_t)scene * P.slot_groups * 2;
+    const double *qp = P.queries + ((int64_t)b * P.Q + q) * 3;
+    const double qx = qp[0], qy = qp[1], qz = qp[2];
+    const int lay = tile_layout(n, P.layout[scene], P.slot_tiles);
+    const bool by_w = lay < 0;
+    const float4 *tsrc = by_w ? P.sorted + (int64_t)scene * P.slot_points : cloud;
+    const TileGeom g(n, lay);
+    const GroupGeom gg(g);
+    const int per = (gg.n_groups + P.segs - 1) / P.segs;
+    const int g_begin = seg * per, g_end = min(gg.n_groups, g_begin + per);
+    float *glb = sGLB[warp];
+    const QueryF qf = make_queryf(qx, qy, qz);
+    TopK e{INFINITY, 0xffffffffu};
+    double bound = INFINITY;
+    for (int c0 = g_begin; c0 < g_end; c0 += KS_GCHUNK) {
+        const int cn = min(KS_GCHUNK, g_end - c0);
+        double ubmin = INFINITY;
+        for (int j = lane; j < cn; j += 32) {
+            const float4 a = knn_ldg(gboxes + 2 * (int64_t)(c0 + j)), h = knn_ldg(gboxes + 2 * (int64_t)(c0 + j) + 1);
+            glb[j] = knn_box_lb32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
+            if (__float_as_int(h.z) >= k)
+                ubmin = fmin(ubmin, (double)knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y));
+        }
+        bound = fmin(bound, warp_min(ubmin));
+        __syncwarp();
+        for (int pick = 0; pick < KS_GPICKS; ++pick) {
+            float best = INFINITY;
+            int bj = -1;
+            for (int j = lane; j < cn; j += 32) {
+                const float v = glb[j];
+                if (v < best) best = v, bj = j; // NaN (visited) never wins
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ob = __shfl_xor_sync(AMPC_FULL_MASK, best, o);
+                const int oj = __shfl_xor_sync(AMPC_FULL_MASK, bj, o);
+                if (ob < best || (ob == best && oj >= 0 && (bj < 0 || oj < bj))) best = ob, bj = oj;
+            }
+            if (bj < 0 || !((double)best <= bound))
+                break;
+            visit_group(P, boxes, tsrc, n, g, gg, c0 + bj, qf, qx, qy, qz, e, bound, k, lane, by_w);
+            __syncwarp();
+            if (lane == 0) glb[bj] = NAN;
+            __syncwarp();
+        }
+        for (int jb = 0; jb < cn; jb += 32) {
+            const float lbv = (jb + lane < cn) ? glb[jb + lane] : NAN;
+            unsigned mk = __ballot_sync(AMPC_FULL_MASK, (double)lbv <= bound);
+            while (mk) {
+                const int src = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const float lbj = __shfl_sync(AMPC_FULL_MASK, lbv, src);
+                if ((double)lbj <= bound) // the bound may have tightened since the ballot
+                    visit_group(P, boxes, tsrc, n, g, gg, c0 + jb + src, qf, qx, qy, qz, e, bound, k, lane, by_w);
             }
         }
         __syncwarp();
