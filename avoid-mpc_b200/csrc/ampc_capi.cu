@@ -534,7 +534,10 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
 
 // sort_mode: the scenes were given layout -1 -> after the NaN filter, bucket a copy of each
 // cloud by Morton cell and build the tile boxes over the copy
-int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaStream_t st, bool sort_mode = false) {
+// row_hint: a row pitch some of these scenes may carry in their layout word besides the handle's
+// own hint (the depth kernels record the image width themselves); only sizes the group pass
+int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaStream_t st, bool sort_mode = false,
+                 int row_hint = 0) {
     int slot;
     int rc = prof_begin(h, SEC_INDEX, st, &slot);
     if (rc) return rc;
@@ -579,8 +582,17 @@ int launch_index(ampc_handle *h, int kind, int first_scene, int n_scenes, cudaSt
         h->launches++;
         CK(cudaGetLastError());
     }
-    // second level: boxes of the groups of 16 tiles
-    group_boxes_kernel<<<dim3(n_scenes, (h->slot_groups[kind] + 7) / 8), 256, 0, st>>>(
+    // second level: boxes of the groups of 16 tiles.  Grid: the most groups a scene of this handle
+    // can have under the layouts in play (linear, the handle's row hint, the caller's row hint)
+    int g_max = GroupGeom(TileGeom(h->slot_points[kind], 0)).n_groups;
+    for (int w : {h->row_w[kind], row_hint})
+        if (w > 0 && tile_layout(h->slot_points[kind], w, h->slot_tiles[kind]) > 0) {
+            // fewer points mean fewer rows, never more groups
+            const int gw = GroupGeom(TileGeom(h->slot_points[kind], w)).n_groups;
+            if (gw > g_max) g_max = gw;
+        }
+    if (g_max > h->slot_groups[kind]) g_max = h->slot_groups[kind];
+    group_boxes_kernel<<<dim3(n_scenes, (g_max + 7) / 8), 256, 0, st>>>(
         h->boxes[kind].as<float4>(), h->gboxes[kind].as<float4>(), h->counts[kind].as<int32_t>(), h->slot_tiles[kind],
         h->slot_groups[kind], h->layout[kind].as<int32_t>(), first_scene);
     h->launches++;
@@ -1329,7 +1341,7 @@ int ampc_depth_set_batch_dev(ampc_handle *h, int32_t first_scene, int32_t n_scen
     }
     rc = prof_end(h, slot, st);
     if (rc) return rc;
-    rc = launch_index(h, AMPC_CLOUD_OBSTACLE, first_scene, n_scenes, st);
+    rc = launch_index(h, AMPC_CLOUD_OBSTACLE, first_scene, n_scenes, st, false, W);
     if (rc || !with_edge) return rc;
     return launch_index(h, AMPC_CLOUD_EDGE, first_scene, n_scenes, st);
 }

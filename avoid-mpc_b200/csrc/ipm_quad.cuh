@@ -85,7 +85,7 @@ struct QuadGmem {
         ut = o, o += 4 * N;
         q = o, o += 10 * (N + 1); // grad_x of the objective, q_k[i] at 10 k + i
         rg = o, o += GF_STAGE * N;
-        Hc = o, o += 36 * N; // cost stage kc, axis a, other axis b at 36kc + 12a + 4b: pp, pv, vp, vv
+        Hc = o, o += 27 * N; // cost stage kc at 27 kc: pp[a][b] at 3a+b, pv[a][b] at 9+3a+b, vv[a][b] at 18+3a+b
         Kg = o, o += 28 * N; // stage k: axis a at 9a (control l, component c at 3l+c), yaw at 27
         cs = o, o += 2 * N;
         fp = o, o += N; // objective of cost stage kc (smoothed)
@@ -353,16 +353,15 @@ __device__ __forceinline__ void eval_item(const SolveConsts &c, const QuadGmem &
         RW(qo, i) = A.g[i];
         RW(qo, 4 + i) = A.g[4 + i];
     }
-    double *ho = G + ((LG.Hc + 36 * kc) << QS);
+    double *ho = G + ((LG.Hc + 27 * kc) << QS);
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
             const int lo = a < b ? a : b, hi = a < b ? b : a;
-            RW(ho, 12 * a + 4 * b + 0) = A.hpp[sym3(lo, hi)];
-            RW(ho, 12 * a + 4 * b + 1) = A.hpv[3 * a + b]; // d2 / dp_a dv_b
-            RW(ho, 12 * a + 4 * b + 2) = A.hpv[3 * b + a]; // d2 / dv_a dp_b
-            RW(ho, 12 * a + 4 * b + 3) = A.hvv[sym3(lo, hi)];
+            RW(ho, 3 * a + b) = A.hpp[sym3(lo, hi)];
+            RW(ho, 9 + 3 * a + b) = A.hpv[3 * a + b]; // d2 / dp_a dv_b
+            RW(ho, 18 + 3 * a + b) = A.hvv[sym3(lo, hi)];
         }
     RW(G, LG.fp + kc) = A.acc;
     RW(G, LG.fd + kc) = A.accd;
@@ -514,11 +513,17 @@ __device__ __forceinline__ bool quad_riccati_backward(const SolveConsts &c, cons
     double yP = 2.0 * c.wgt[3] + delta, ypv = *py;
     const double *pc = S + ((QF_STAGE * (N - 1) + a) << QS); // this lane's control block
     const double *pc3 = S + ((QF_STAGE * (N - 1) + 3) << QS); // the yaw control block
-    const double *hp = G + ((LG.Hc + 36 * (N > 1 ? N - 2 : 0) + 12 * aa) << QS);
+    // row aa of pp / pv / vv at hrow + {0, 9, 18} + b, column aa of pv at hcol + 3 b
+    const double *hrow = G + ((LG.Hc + 27 * (N > 1 ? N - 2 : 0) + 3 * aa) << QS);
+    const double *hcol = G + ((LG.Hc + 27 * (N > 1 ? N - 2 : 0) + 9 + aa) << QS);
     double n_H[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i)
-        n_H[i] = N > 1 ? RW(hp, i) : 0.0;
+    for (int b = 0; b < 3; ++b) {
+        n_H[4 * b + 0] = N > 1 ? RW(hrow, b) : 0.0;
+        n_H[4 * b + 1] = N > 1 ? RW(hrow, 9 + b) : 0.0;
+        n_H[4 * b + 2] = N > 1 ? RW(hcol, 3 * b) : 0.0;
+        n_H[4 * b + 3] = N > 1 ? RW(hrow, 18 + b) : 0.0;
+    }
     pq -= 10 << QS; // q_{N-1}
     py -= 10 << QS;
     double n_q[4], n_r = *pr, n_r3 = *pr3;
@@ -539,10 +544,15 @@ __device__ __forceinline__ bool quad_riccati_backward(const SolveConsts &c, cons
             pr3 -= GF_STAGE << QS;
             n_r = *pr, n_r3 = *pr3;
             if (k > 1) {
-                hp -= 36 << QS;
+                hrow -= 27 << QS;
+                hcol -= 27 << QS;
 #pragma unroll
-                for (int i = 0; i < 12; ++i)
-                    n_H[i] = RW(hp, i);
+                for (int b = 0; b < 3; ++b) {
+                    n_H[4 * b + 0] = RW(hrow, b);
+                    n_H[4 * b + 1] = RW(hrow, 9 + b);
+                    n_H[4 * b + 2] = RW(hcol, 3 * b);
+                    n_H[4 * b + 3] = RW(hrow, 18 + b);
+                }
                 pq -= 10 << QS;
                 py -= 10 << QS;
                 n_q[0] = RW(pq, 0), n_q[1] = RW(pq, 4), n_q[2] = RW(pq, 7), n_q[3] = *py;
@@ -698,6 +708,9 @@ struct BarAcc {
 // ---- loop 3, stages 0 .. N-1.  With `forward`: the forward sweep du_k = K_k dx_k + kff_k,
 // dx_{k+1} = Phi dx_k + Gam du_k, the multiplier step length (IPOPT eq. (15)) and the first
 // trial point (alpha = 1) in one go; without: a shorter trial along the stored step.
+// (x_t = x + roll-out of the step, NOT a fresh roll-out of u_t: measured, the fresh roll-out
+// re-rounds the whole trajectory, and that noise (1e-14 in x, 1e-11 in f) exceeds the Armijo
+// slack near convergence -- +4 % iterations, +10 % time.)
 // Trial point of the projected line search: u_t = u + clip(alpha du) per component
 // (fraction-to-the-boundary rule), x_t = x + roll-out of the clipped step (by linearity),
 // written to the other x buffer / the trial controls for quads with `on`; Armijo slope

@@ -415,6 +415,7 @@ __device__ __noinline__ double adjoint_dual_inf(const WarpCtx &w) {
         v1::chain_FT(fi, lv, fl);
         lv[0] = qk0 + fl[0], lv[1] = qk1 + fl[1], lv[2] = qk2 + fl[2];
     }
+    __syncwarp(); // q, r may be rewritten by the next evaluation
     return warp_max(e_dual);
 }
 
@@ -643,8 +644,10 @@ __device__ __noinline__ void rollout_delta(const WarpCtx &w) {
     __syncwarp();
 }
 
+// has_work = false: a warp of the CTA without an instance; it only keeps the CTA's per-iteration
+// barrier company (every warp of a CTA executes that ONE barrier the same number of times)
 template <bool SYNC>
-__device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out) {
+__device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out, bool has_work) {
     const SolveConsts &c = *w.c;
     const int N = c.N, lane = w.lane, nu = 4 * N;
     double *s = w.s;
@@ -656,7 +659,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
     int n_reg = 0, n_bt = 0;
 
     // controls from the warm start pushed into the box interior; cos/sin of the ref yaw
-    for (int e = lane; e < nu; e += 32) {
+    for (int e = lane; has_work && e < nu; e += 32) {
         const int k = e >> 2, i = e & 3;
         const double lo = c.lb[i], hi = c.ub[i];
         double pl = fmin(c.bound_push * fmax(1.0, fabs(lo)), c.bound_frac * (hi - lo));
@@ -670,15 +673,15 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
     }
     for (int e = lane; e < 48 * N; e += 32)
         s[L.Kg + e] = 0.0;
-    for (int k = lane; k < N; k += 32) {
+    for (int k = lane; has_work && k < N; k += 32) {
         const double yaw = w.prefix[10 + 10 * k + 3];
         s[L.cs + 2 * k] = cos(yaw);
         s[L.cs + 2 * k + 1] = sin(-yaw);
     }
-    if (lane < 10)
+    if (lane < 10 && has_work)
         s[L.x + lane] = w.prefix[lane];
     __syncwarp();
-    for (int k = 0; k < N; ++k) { // roll-out
+    for (int k = 0; has_work && k < N; ++k) { // roll-out
         if (lane < 10)
             s[L.x + 10 * (k + 1) + lane] = c.gam[lane] + phi_row_dot(c.Phi, lane, s + L.x + 10 * k) +
                                            gam_row_dot(c.Gam, lane, s + L.u + 4 * k);
@@ -687,12 +690,21 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
 
     int status = 1, iter = 0;
     double e_dual = 0.0, e_compl = 0.0;
-    for (iter = 0;; ++iter) {
+    bool done = !has_work;
+    for (iter = 0;;) {
         // the warps of a CTA start every iteration together, so that they run the same code
         // region at the same time and share the instruction cache (the kernel's code is far
-        // larger than it); warps that have finished have exited and no longer count
-        if (SYNC)
-            __syncthreads_or(1); // finished warps keep voting 0 at this barrier (see the kernel)
+        // larger than it).  A warp that has finished (or never had an instance) keeps arriving
+        // at this one barrier, voting "done", until every warp of the CTA votes "done".
+        if (SYNC) {
+            if (!__syncthreads_or(done ? 0 : 1))
+                break;
+        } else if (done) {
+            break;
+        }
+        if (done)
+            continue;
+        const bool finished = [&]() -> bool {
         double eps = 0.0, f = 0.0, c_mu = 0.0, delta = 0.0;
         bool stop = false;
         // pass 0: evaluate, test convergence, update mu (IPOPT eq. (7)); if mu changed, the
@@ -754,7 +766,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
                 break;
         }
         if (stop)
-            break;
+            return true;
         // Newton system with inertia correction (IPOPT Algorithm IC schedule)
         {
             int ntry = 0;
@@ -772,7 +784,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
             }
         }
         if (stop)
-            break;
+            return true;
         if (delta > 0.0) {
             delta_last = delta;
             ++n_reg;
@@ -837,7 +849,7 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         }
         if (!accepted) {
             status = 2;
-            break;
+            return true;
         }
         for (int e = lane; e < nu; e += 32) {
             const int i = e & 3;
@@ -861,7 +873,15 @@ __device__ void solve_instance(const WarpCtx &w, double *w_inout, SolveOut *out)
         for (int e = 10 + lane; e < 10 * (N + 1); e += 32)
             s[L.x + e] += s[L.dxt + e];
         __syncwarp();
+        return false;
+        }();
+        if (finished)
+            done = true;
+        else
+            ++iter;
     }
+    if (!has_work)
+        return;
     // results: w = [X_0,U_0,...,X_N]; objective without smoothing
     const double cost = eval_value(w, 0.0, false);
     for (int e = lane; e < 10 * (N + 1); e += 32) {
@@ -902,18 +922,13 @@ ipm_solve_kernel(const __grid_constant__ SolveConsts consts, int B, const double
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * WARPS + warp;
-    if (!(b >= B || (active && active[b] == 0))) {
-        const WarpLayout L(sc->N);
-        WarpCtx ctx(sc, wbase + (size_t)warp * L.total, prefix + (size_t)b * sc->n_prefix, lane);
-        solve_instance<(WARPS > 1)>(ctx, w_inout + (size_t)b * (10 + 14 * sc->N), info + b);
-    }
-    // The warps of a CTA meet at a barrier at the top of every iteration.  A warp without work, or
-    // one that has finished, keeps arriving at that barrier (voting "done") until every warp of
-    // the CTA votes "done": all threads execute the same number of barriers, none is skipped by
-    // an exited warp.
-    if (WARPS > 1)
-        while (__syncthreads_or(0)) {
-        }
+    const bool has_work = !(b >= B || (active && active[b] == 0));
+    if (WARPS == 1 && !has_work)
+        return;
+    const int bb = has_work ? b : 0; // a warp without work only attends the CTA's barrier
+    const WarpLayout L(sc->N);
+    WarpCtx ctx(sc, wbase + (size_t)warp * L.total, prefix + (size_t)bb * sc->n_prefix, lane);
+    solve_instance<(WARPS > 1)>(ctx, w_inout + (size_t)bb * (10 + 14 * sc->N), info + bb, has_work);
 }
 
 } // namespace v1

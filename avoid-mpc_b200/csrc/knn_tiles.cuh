@@ -896,35 +896,36 @@ __global__ void __launch_bounds__(256)
 group_boxes_kernel(const float4 *__restrict__ boxes, float4 *__restrict__ gboxes, const int32_t *__restrict__ counts,
                    int64_t slot_tiles, int64_t slot_groups, const int32_t *__restrict__ layout, int first_scene) {
     const int scene = first_scene + blockIdx.x;
-    const int lane = threadIdx.x & 31, g = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     const int n = counts[scene];
     const TileGeom tg(n, tile_layout(n, layout[scene], slot_tiles));
     const GroupGeom gg(tg);
-    if (g >= gg.n_groups)
-        return;
     const float4 *bx = boxes + (int64_t)scene * slot_tiles * 2;
-    int ty, tx;
-    const int t = lane < KG_TILES ? gg.tile(g, lane, ty, tx) : -1;
-    float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
-    int cnt = 0;
-    if (t >= 0) {
-        const float4 a = bx[2 * (int64_t)t], h = bx[2 * (int64_t)t + 1];
-        lx = a.x, ly = a.y, lz = a.z, hx = a.w, hy = h.x, hz = h.y, cnt = __float_as_int(h.z);
-    }
+    // the grid is sized for the common layouts; a scene with more groups is covered by the stride
+    for (int g = blockIdx.y * 8 + (threadIdx.x >> 5); g < gg.n_groups; g += gridDim.y * 8) {
+        int ty, tx;
+        const int t = lane < KG_TILES ? gg.tile(g, lane, ty, tx) : -1;
+        float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+        int cnt = 0;
+        if (t >= 0) {
+            const float4 a = bx[2 * (int64_t)t], h = bx[2 * (int64_t)t + 1];
+            lx = a.x, ly = a.y, lz = a.z, hx = a.w, hy = h.x, hz = h.y, cnt = __float_as_int(h.z);
+        }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) {
-        lx = fminf(lx, __shfl_xor_sync(AMPC_FULL_MASK, lx, o));
-        ly = fminf(ly, __shfl_xor_sync(AMPC_FULL_MASK, ly, o));
-        lz = fminf(lz, __shfl_xor_sync(AMPC_FULL_MASK, lz, o));
-        hx = fmaxf(hx, __shfl_xor_sync(AMPC_FULL_MASK, hx, o));
-        hy = fmaxf(hy, __shfl_xor_sync(AMPC_FULL_MASK, hy, o));
-        hz = fmaxf(hz, __shfl_xor_sync(AMPC_FULL_MASK, hz, o));
-        cnt += __shfl_xor_sync(AMPC_FULL_MASK, cnt, o);
-    }
-    if (lane == 0) {
-        float4 *dst = gboxes + ((int64_t)scene * slot_groups + g) * 2;
-        dst[0] = make_float4(lx, ly, lz, hx);
-        dst[1] = make_float4(hy, hz, __int_as_float(cnt), 0.f);
+        for (int o = 8; o > 0; o >>= 1) {
+            lx = fminf(lx, __shfl_xor_sync(AMPC_FULL_MASK, lx, o));
+            ly = fminf(ly, __shfl_xor_sync(AMPC_FULL_MASK, ly, o));
+            lz = fminf(lz, __shfl_xor_sync(AMPC_FULL_MASK, lz, o));
+            hx = fmaxf(hx, __shfl_xor_sync(AMPC_FULL_MASK, hx, o));
+            hy = fmaxf(hy, __shfl_xor_sync(AMPC_FULL_MASK, hy, o));
+            hz = fmaxf(hz, __shfl_xor_sync(AMPC_FULL_MASK, hz, o));
+            cnt += __shfl_xor_sync(AMPC_FULL_MASK, cnt, o);
+        }
+        if (lane == 0) {
+            float4 *dst = gboxes + ((int64_t)scene * slot_groups + g) * 2;
+            dst[0] = make_float4(lx, ly, lz, hx);
+            dst[1] = make_float4(hy, hz, __int_as_float(cnt), 0.f);
+        }
     }
 }
 
