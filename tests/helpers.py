@@ -33,3 +33,40 @@ def oracle_solve_batch(N, K, dt, params, W0, **opts):
     it = np.array([i.iters for i in infos])
     cost = np.array([i.cost for i in infos])
     return W, st, it, cost
+
+
+def golden2_groups():
+    """tests/golden/solve_golden2.npz regrouped by shape: {(N, K): dict(ids, params, W0, w, w_cert,
+    cert, stage, cost, sid)} with the parameter vectors rebuilt from the stored seeds exactly as
+    tests/golden/make_solve_golden2.py built them (synthetic scene -> oracle k-NN -> packing)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "solve_golden2.npz"))
+    groups = {}
+    for i, (sid, N, K, npts, ref_warm, stage) in enumerate(G["meta"].tolist()):
+        groups.setdefault((N, K, npts), []).append(i)
+    out = {}
+    for (N, K, npts), ids in groups.items():
+        sids = [int(G["meta"][i, 0]) for i in ids]
+        inst = make_instances(sids, N, K, npts)
+        W0 = np.stack([S.warm_start("ref" if G["meta"][i, 4] else "cold", inst["x0"][j], inst["ref"][j], N)
+                       for j, i in enumerate(ids)])
+        nw = 10 + 14 * N
+        out[(N, K)] = dict(ids=ids, sid=sids, params=inst["params"], prefix=inst["prefix"], W0=W0,
+                           w=G["w"][ids, :nw], w_cert=G["w_cert"][ids, :nw], cert=G["cert"][ids],
+                           stage=G["meta"][ids, 5], cost=G["cost"][ids])
+    return out
+
+
+def golden2_classify(W, g, tol=1e-4):
+    """Per instance of a golden2 group: 'same' (within tol of the independent optimum),
+    'certified' (another basin: within tol of a point an independent epigraph solve, started at
+    this algorithm's optimum, confirmed as a KKT point), else 'open'."""
+    out = []
+    for j in range(len(g["ids"])):
+        if g["stage"][j] > 0 and np.abs(W[j] - g["w"][j]).max() < tol:
+            out.append("same")
+        elif g["cert"][j] == 1 and np.abs(W[j] - g["w_cert"][j]).max() < tol:
+            out.append("certified")
+        else:
+            out.append("open")
+    return out

@@ -39,15 +39,20 @@ def test_solve_matches_oracle(N, K, npts, kind):
     h = A.Handle(N=N, K=K, dt=dt, max_batch=B, max_points=16)
     W, info = h.solve(inst["prefix"], W0)
     oW, ost, oit, ocost = oracle_solve_batch(N, K, dt, inst["params"], W0)
+    # Same algorithm on both sides: EVERY instance must end with the same status, iteration count
+    # and point.  Allow-list of known divergences (scene id -> reason): empty -- tools/
+    # enumerate_mismatch.py found none on these 4 x 48 instances with either kernel (worst l_inf
+    # 1e-13); an entry here needs the two iterate histories that explain it.
+    ALLOW = {}
+    bad = [200 + b for b in range(B) if (200 + b) not in ALLOW and
+           (info["status"][b] != ost[b] or info["iters"][b] != oit[b] or np.abs(W[b] - oW[b]).max() >= TIGHT_TOL)]
+    assert not bad, f"GPU and oracle disagree on scenes {bad}"
     both = (info["status"] == 0) & (ost == 0)
     assert both.mean() >= 0.9, f"converged on both sides: {both.mean():.2f}"
     err = np.abs(W - oW).max(axis=1)
-    same = err[both] < TRAJ_TOL
-    # identical algorithm: every instance converged on both sides lands on the same optimum
-    assert same.mean() >= 0.98, f"same optimum fraction {same.mean():.3f}, worst {err[both].max():.2e}"
-    assert np.median(err[both]) < TIGHT_TOL
+    assert err[both].max() < TIGHT_TOL
     rel = np.abs(info["cost"][both] - ocost[both]) / np.maximum(1.0, np.abs(ocost[both]))
-    assert np.median(rel) < 1e-9
+    assert rel.max() < 1e-9
     # KKT residuals reported by the kernel
     assert (info["kkt_dual"][info["status"] == 0] <= 1e-8).all()
     assert (info["kkt_compl"][info["status"] == 0] <= 1e-8).all()
