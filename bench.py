@@ -188,6 +188,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "window": "the timed region of `value`"}
 
 
+HOST_BINDING = {}
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Run this process (and so first-touch its pinned host buffers) on the CPUs of the NUMA node the
+    GPU hangs off, as a deployment would with numactl: with one process per GPU on a two-socket
+    host, host->device copies otherwise cross the socket link.  Best effort; recorded in the line."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            HOST_BINDING.update(numa_node=None, note="the GPU reports no NUMA node")
+            return
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            HOST_BINDING.update(numa_node=node, cpus=len(cpus), pci=bdf)
+    except Exception as e:  # no sysfs / no permission: run unbound
+        HOST_BINDING.update(numa_node=None, note="unbound (%s)" % type(e).__name__)
+
+
 def dist_setup():
     import torch
     import torch.distributed as dist
@@ -197,8 +223,11 @@ def dist_setup():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    if os.environ.get("AMPC_BENCH_NUMA_BIND", "1") != "0":
+        bind_to_gpu_numa_node(torch, local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     return torch, dist, world, rank, local, dev
 
@@ -461,16 +490,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def e2e_leg(A, torch, dist, dev, local, world, args, rows=200, cols=250, distinct=128, lanes_n=3):
+def e2e_leg(A, torch, dist, dev, local, world, args, rows=200, cols=250, distinct=128, lanes_n=6, batches_per_call=2):
     """`e2e`: the same round through the host-buffer C-ABI, starting from what the reference's ingress
     receives -- the depth frame (FrameKDMap::AddVertex, src/FrameKDMap.cpp:34-52): every step copies its
     depth frames (f32 metres, 4 bytes per point) and states from pinned host memory, builds both clouds
     and their indices on the device, runs k-NN + solve, and reads trajectories / costs / status back.
-    `lanes_n` host threads each drive their own handle, so one batch's upload overlaps the compute of
-    the others.  `cloud_upload` is the same with ready-made 16-byte clouds uploaded instead."""
+    `lanes_n` host threads each drive their own handle (calls of `batches_per_call` x --batch
+    instances), so one call's upload overlaps the compute of the others; measured on one B200:
+    3 / 6 / 8 lanes of 1024 -> 156 k / 186 k / 204 k solves/s, 6 lanes of 2048 -> 202 k at 41 GB/s
+    host->device, which is what a pinned copy alone reaches on that box (42-50 GB/s): PCIe-bound.
+    `depth_u16` is the same from CV_16UC1 frames (half the bytes), `cloud_upload` the same with
+    ready-made 16-byte clouds uploaded instead."""
     from concurrent.futures import ThreadPoolExecutor
     D, S = A.defaults, A.synth
-    B = args.batch
+    B = args.batch * batches_per_call
     rank = int(os.environ.get("RANK", "0"))
     cam = dict(fx=cols / 2, fy=cols / 2, cx=cols / 2, cy=rows / 2, resize_scale=1.0)
     ids = [rank * B + b for b in range(B)]
@@ -517,7 +550,7 @@ def e2e_leg(A, torch, dist, dev, local, world, args, rows=200, cols=250, distinc
         ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
                                 safety_distance=D.SAFETY_DISTANCE)    # H2D states, k-NN, solve, D2H results
 
-    n = max(12, min(args.steps, 24))
+    n = max(4 * lanes_n, min(args.steps, 24))
     dt = run(depth_step, lanes, n)
     info = lanes[0]["info_h"].numpy().view(A.capi.INFO_DTYPE).reshape(B)
     h2d = depth_h.numel() * 4 + T_np.nbytes + (x0_h.numel() + ref_h.numel() + w0_h.numel()) * 8
@@ -527,7 +560,28 @@ def e2e_leg(A, torch, dist, dev, local, world, args, rows=200, cols=250, distinc
            "converged_frac": float((info["status"] == 0).mean()),
            "ingress": "host depth frames %dx%d f32 (what FrameKDMap::AddVertex receives); Obstacle + Edge clouds and "
                       "their indices are built on the device" % (rows, cols),
-           "h2d_GBps": h2d * n / dt / 1e9}
+           "h2d_GBps": h2d * n / dt / 1e9, "host_binding": dict(HOST_BINDING)}
+    # the same from CV_16UC1 frames in millimetres (what a depth camera publishes; the reference's
+    # GetInvDepthImg<uint16_t> branch, src/FrameKDMap.cpp:96-97, pixel2meter 0.001): half the bytes
+    depth16_h = torch.from_numpy(np.clip(np.rint(depth_h.numpy() * 1000.0), 0, 65535).astype(np.uint16).view(np.int16)).pin_memory()
+    depth16_np = depth16_h.numpy().view(np.uint16)
+    for ln in lanes:
+        ln["h"].set_camera(pixel2meter=0.001, **cam)
+
+    def depth16_step(ln):
+        ln["w_h"].copy_(w0_h)
+        ln["h"].depth_set_batch(depth16_np, T_np)
+        ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
+                                safety_distance=D.SAFETY_DISTANCE)
+
+    dt16 = run(depth16_step, lanes, n)
+    h2d16 = h2d - depth_h.numel() * 2
+    out["depth_u16"] = {"value": world * B * n / dt16, "unit": UNIT, "h2d_bytes_per_step": h2d16, "d2h_bytes_per_step": d2h,
+                        "steps": n, "h2d_GBps": h2d16 * n / dt16 / 1e9,
+                        "note": "CV_16UC1 millimetre frames (a depth camera's format, pixel2meter 0.001) instead of the "
+                                "simulator's CV_32FC1 metres: half the host->device bytes"}
+    for ln in lanes:
+        ln["h"].set_camera(**cam)
     # the same with ready-made clouds uploaded (16 bytes per point): the number round 1 called e2e
     clouds_h = torch.empty((B, rows * cols, 4), dtype=torch.float32).pin_memory()
     clouds_h.copy_(S.forest_clouds_torch(ids, rows * cols, dev))
@@ -540,7 +594,7 @@ def e2e_leg(A, torch, dist, dev, local, world, args, rows=200, cols=250, distinc
         ln["h"].round_host_ptrs(B, x0_h, ref_h, ln["w_h"], ln["info_h"], ln["replan_h"], speed=D.SPEED,
                                 safety_distance=D.SAFETY_DISTANCE)
 
-    n2 = max(6, min(args.steps, 12))
+    n2 = 2 * lanes_n
     dt2 = run(cloud_step, lanes, n2)
     h2d2 = clouds_h.numel() * 4 + (x0_h.numel() + ref_h.numel() + w0_h.numel()) * 8
     out["cloud_upload"] = {"value": world * B * n2 / dt2, "unit": UNIT, "h2d_bytes_per_step": h2d2,

@@ -70,3 +70,40 @@ def golden2_classify(W, g, tol=1e-4):
         else:
             out.append("open")
     return out
+
+
+# solve_golden2.npz: the instances on which this repository's algorithm (oracle and CUDA alike) does
+# NOT land within 1e-4 of an independently computed or independently certified optimum, by cause.
+GOLDEN2_KINK = {1192, 1275}          # minimiser on the |v.n| kink: one control differs by 1.4e-4 / 1.5e-4 (cost by 1e-5)
+GOLDEN2_OTHER_KKT = {1081, 1105, 1191, 1242, 1329}  # converged (KKT <= 1e-8 of the smoothed problem); the epigraph solve
+#   started AT this point leaves it for another KKT point 5e-3 .. 0.95 away -- of HIGHER cost for four of them
+#   (+6.2, +0.06, +0.005, +0.56) and 0.07 % lower for 1329; the independent cold solve ends in a third basin
+GOLDEN2_POOR_LOCAL = {1353}  # ends at a stationary point of cost 1577.8 (oracle: stalls there at KKT 4e-8 until its
+#   100-iteration cap; CUDA: converges there in 41 iterations, same point to 1e-13); the epigraph solve started AT it
+#   escapes to the independent optimum, cost 17.2 -- the one instance of 512 where this algorithm is clearly worse
+
+
+def golden2_check(N, K, g, W, status, cost, f_eval):
+    """The assertions both golden2 tests make; returns the class counts."""
+    cl = golden2_classify(W, g)
+    counts = {"same": 0, "certified": 0, "kink": 0, "other_kkt": 0, "poor_local": 0}
+    for j, c in enumerate(cl):
+        sid = g["sid"][j]
+        if c != "open":
+            counts[c] += 1
+            assert sid not in GOLDEN2_KINK | GOLDEN2_OTHER_KKT | GOLDEN2_POOR_LOCAL, ("stale allow-list entry", sid)
+            if c == "same":
+                assert abs(cost[j] - g["cost"][j]) <= 1e-6 * abs(g["cost"][j]), sid
+        elif sid in GOLDEN2_KINK:
+            counts["kink"] += 1
+            assert status[j] == 0 and np.abs(W[j] - g["w"][j]).max() < 2e-4, sid
+            assert abs(cost[j] - g["cost"][j]) <= 1e-7 * abs(g["cost"][j]), sid
+        elif sid in GOLDEN2_OTHER_KKT:
+            counts["other_kkt"] += 1
+            assert status[j] == 0 and g["cert"][j] == 1, sid
+            assert cost[j] <= 1.001 * f_eval(N, K, g["w_cert"][j], g["params"][j]), sid
+        else:
+            assert sid in GOLDEN2_POOR_LOCAL, ("unexplained mismatch against solve_golden2.npz", sid, N, K)
+            counts["poor_local"] += 1
+            assert status[j] in (0, 1) and abs(cost[j] - 1577.792789) < 1e-5, sid
+    return counts
