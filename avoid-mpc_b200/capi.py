@@ -190,17 +190,35 @@ class Handle:
         if rc:
             raise AmpcError(rc, self.L.ampc_last_error(None).decode())
         self.h = h
-        if defaults:  # the shipped mpc_parameters.yaml values
-            from . import defaults as D
-            self.set_weights(D.WEIGHTS)
-            self.set_tau(D.TAU)
-            self.set_gains(D.GAINS)
-            self.set_radius(D.DRONE_RADIUS)
-            self.set_accel_limits(D.A_MIN_Z, D.A_MAX_Z, D.A_MAX_XY, D.A_MAX_YAW_DOT)
+        if defaults:
+            self._shipped_parameters()
+
+    @classmethod
+    def borrowed(cls, ptr, N, K, dt, defaults=True):
+        """View of an ampc_handle* owned by someone else (e.g. a device of ampc_multi): never destroyed here."""
+        self = cls.__new__(cls)
+        self.L = lib()
+        self.N, self.K, self.dt = N, K, dt
+        self.n_w = 10 + 14 * N
+        self.n_prefix = 20 + 10 * N + 3 * K * N
+        self.h = _vp(ptr)
+        self._borrowed = True
+        if defaults:
+            self._shipped_parameters()
+        return self
+
+    def _shipped_parameters(self):  # the shipped mpc_parameters.yaml values
+        from . import defaults as D
+        self.set_weights(D.WEIGHTS)
+        self.set_tau(D.TAU)
+        self.set_gains(D.GAINS)
+        self.set_radius(D.DRONE_RADIUS)
+        self.set_accel_limits(D.A_MIN_Z, D.A_MAX_Z, D.A_MAX_XY, D.A_MAX_YAW_DOT)
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.ampc_destroy(self.h)
+            if not getattr(self, "_borrowed", False):
+                self.L.ampc_destroy(self.h)
             self.h = None
 
     __del__ = close

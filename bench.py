@@ -292,9 +292,14 @@ def run_ours(args):
         ln["info"] = torch.zeros((BL, 48), dtype=torch.uint8, device=dev)
         ln["info_f64"] = ln["info"].view(torch.float64).view(BL, 6)
         ln["replan"] = torch.zeros(BL, dtype=torch.int32, device=dev)
-        ln["costs"] = torch.zeros(BL, dtype=torch.float64, device=dev)
-        ln["gathered"] = torch.zeros(BL * world, dtype=torch.float64, device=dev) if world > 1 else None
+        # cost exchange, double buffered: the all-gather of step s runs on its own stream while the
+        # lane already computes step s+1 (it only has to be over before step s+2 reuses the buffer)
+        ln["costs"] = [torch.zeros(BL, dtype=torch.float64, device=dev) for _ in range(2)]
+        ln["gathered"] = [torch.zeros(BL * world, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+        ln["gather_done"] = [None, None]
+        ln["k"] = 0
         lanes.append(ln)
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
     h = lanes[0]["h"]
     l0_ = lanes[0]
     x0, ref, w0, w, info, replan = l0_["x0"], l0_["ref"], l0_["w0"], l0_["w"], l0_["info"], l0_["replan"]
@@ -310,9 +315,22 @@ def run_ours(args):
             ln["h"].cloud_index_dev(0, n, stream=st.cuda_stream)
             ln["h"].round_dev(n, ln["x0"], ln["ref"], ln["w"], info_dev=ln["info"], replan_dev=ln["replan"], speed=D.SPEED,
                               safety_distance=D.SAFETY_DISTANCE, stream=st.cuda_stream)
-            if world > 1 and n == BL:  # per-instance best-cost exchange: the only collective of the path
-                ln["costs"].copy_(ln["info_f64"][:, 0])
-                dist.all_gather_into_tensor(ln["gathered"], ln["costs"])
+            if world > 1 and n == BL and os.environ.get("AMPC_BENCH_GATHER") != "off":  # per-instance cost exchange: the only collective of the path
+                k = ln["k"] & 1
+                ln["k"] += 1
+                if ln["gather_done"][k] is not None:
+                    st.wait_event(ln["gather_done"][k])
+                ln["costs"][k].copy_(ln["info_f64"][:, 0])
+                if os.environ.get("AMPC_BENCH_GATHER", "async") == "inline":  # round 1: on the lane's own stream
+                    dist.all_gather_into_tensor(ln["gathered"][k], ln["costs"][k])
+                else:
+                    ready = torch.cuda.Event()
+                    ready.record(st)
+                    comm.wait_event(ready)
+                    with torch.cuda.stream(comm):
+                        dist.all_gather_into_tensor(ln["gathered"][k], ln["costs"][k])
+                        ln["gather_done"][k] = torch.cuda.Event()
+                        ln["gather_done"][k].record(comm)
 
     def step(n=None):
         if n is None:
@@ -337,6 +355,8 @@ def run_ours(args):
             step(n)
         for ln in lanes:
             main.wait_stream(ln["st"])
+        if comm is not None:
+            main.wait_stream(comm)
         e1.record(main)
         barrier()
         return e0.elapsed_time(e1)
@@ -375,12 +395,19 @@ def run_ours(args):
             prof[k][1] += pr[k][1]
         ln["h"].profile_enable(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    info_np, sstats = solver_stats(A, torch.cat([ln["info"] for ln in lanes]))
+    # scaling trace: every rank's own device time and solver work for the timed region (weak scaling:
+    # each rank has different scenes, the job lasts as long as the rank with the most work)
+    mine = torch.tensor([total_ms, float(info_np["iters"].astype(np.float64).sum())], dtype=torch.float64, device=dev)
+    per_rank = [mine.clone() for _ in range(world)]
     if world > 1:
+        dist.all_gather(per_rank, mine)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_rank = {"device_ms": [float(x[0].item()) for x in per_rank],
+                "solver_iterations_per_step": [float(x[1].item()) for x in per_rank]}
     total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     value = world * BF * args.steps / (total_ms * 1e-3)
-    info_np, sstats = solver_stats(A, torch.cat([ln["info"] for ln in lanes]))
     sstats["need_replan_frac"] = float(torch.cat([ln["replan"] for ln in lanes]).float().mean().item())
     # per-kernel device time per call (with several lanes the kernels of different lanes time-share the GPU)
     index_ms, knn_ms, solve_ms = (prof[k][0] / max(prof[k][1], 1) for k in ("index", "knn", "solve"))
@@ -459,10 +486,13 @@ def run_ours(args):
                 "step": "one control round (index build + k-NN + solve) over %d batches of %d instances, each batch with "
                         "its own %d-point scenes, submitted as %d call(s) on %d CUDA stream(s); the solve kernel refills "
                         "its warps from a queue over all instances of a call" % (F, B, npts, L, L),
-                "timed_region_s": total_ms * 1e-3, "load_steps_before": n_load,
+                "timed_region_s": total_ms * 1e-3, "load_steps_before": n_load, "per_rank": per_rank,
                 "parallelism": f"scene-sharded x{world}",
                 "l2": "inputs larger than L2 (%.1f GB of clouds per step per GPU)" % (BF * npts * 16 / 1e9),
-                "collective": "all_gather of per-instance costs (NCCL), every step" if world > 1 else "none"},
+                "collective": ("all_gather of per-instance costs (NCCL), every step, %s" % (
+                    "on the lane's stream" if os.environ.get("AMPC_BENCH_GATHER", "async") == "inline"
+                    else "SKIPPED (scaling-trace run, not a bench line)" if os.environ.get("AMPC_BENCH_GATHER") == "off"
+                    else "on its own stream one step behind the lanes")) if world > 1 else "none"},
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,

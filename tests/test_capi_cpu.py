@@ -27,6 +27,21 @@ def test_exports_every_declared_symbol(lib):
     assert lib.ampc_api_version() == 1
 
 
+def test_multi_device_library_exports_every_declared_symbol(lib):
+    """include/ampc_multi.h -> libampc_multi.so (host C++ + NCCL over libampc's C-ABI)."""
+    hdr = open(os.path.join(ROOT, "include", "ampc_multi.h")).read()
+    declared = set(re.findall(r"\b(ampc_multi_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(A.multi.SYMBOLS), declared ^ set(A.multi.SYMBOLS)
+    L = A.multi.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libampc_multi.so does not export {name}"
+    import torch
+    if not torch.cuda.is_available():  # no device: creation fails loudly with the CUDA error code
+        with pytest.raises(A.AmpcError) as ei:
+            A.multi.MultiHandle([0], max_batch=4, max_points=64)
+        assert ei.value.code == A.capi.ERR_CUDA
+
+
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(A.capi.Config) == 40
     assert ctypes.sizeof(A.capi.SolverOpts) == 64
