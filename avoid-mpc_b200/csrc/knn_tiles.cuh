@@ -186,6 +186,22 @@ __device__ __forceinline__ float warp_fmax(float v) {
     return ord2f(__reduce_max_sync(AMPC_FULL_MASK, f2ord(v)));
 }
 
+// Non-negative floats (and +inf) order like their bit patterns: warp minimum in ONE redux.sync
+// instead of five shuffle steps.  The sign bit is masked so that a -0 cannot win or lose wrongly;
+// a NaN (0x7fc00000) is larger than +inf and never the minimum unless every lane holds one.
+__device__ __forceinline__ unsigned fbits_nonneg(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+__device__ __forceinline__ float warp_min_nonneg(float v) {
+    return __uint_as_float(__reduce_min_sync(AMPC_FULL_MASK, fbits_nonneg(v)));
+}
+// arg-min over the lanes of a non-negative float, ties to the smallest `idx` (idx >= 0; a lane
+// without a candidate passes idx = INT_MAX): two redux.sync.  Returns the minimum, idx in `bi`.
+__device__ __forceinline__ float warp_argmin_nonneg(float v, int idx, int &bi) {
+    const unsigned mine = fbits_nonneg(v);
+    const unsigned m = __reduce_min_sync(AMPC_FULL_MASK, mine);
+    bi = (int)__reduce_min_sync(AMPC_FULL_MASK, mine == m ? (unsigned)idx : 0x7fffffffu);
+    return __uint_as_float(m);
+}
+
 __device__ __forceinline__ void tile_box_store(float4 *boxes, int64_t tile, float4 p0, float4 p1,
                                                bool v0, bool v1, int lane) {
     // empty slots and NaN coordinates drop out: fminf/fmaxf return the non-NaN operand
@@ -1003,29 +1019,20 @@ __device__ __forceinline__ void visit_group(const KnnParams &P, const float4 *bo
                                             double qy, double qz, TopK &e, double &bound, int k, int lane, bool by_w) {
     int ty, tx;
     const int t = lane < KG_TILES ? gg.tile(G, lane, ty, tx) : -1;
-    float lb = INFINITY;
-    double ub = INFINITY;
+    float lb = INFINITY, ub = INFINITY;
     if (t >= 0) {
         const float4 a = knn_ldg(boxes + 2 * (int64_t)t), h = knn_ldg(boxes + 2 * (int64_t)t + 1);
         lb = knn_box_lb32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
         if (__float_as_int(h.z) >= k) // the tile alone holds >= k points within its farthest corner
-            ub = (double)knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
+            ub = knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
     }
-    bound = fmin(bound, warp_min(ub));
+    bound = fmin(bound, (double)warp_min_nonneg(ub));
     // lanes with a tile still to visit; an empty tile (lb = +inf) never is -- `bound` itself is
     // +inf while fewer than k points have been seen, so "lb <= bound" alone would not end
     bool live = t >= 0 && lb < INFINITY;
     if (!live) lb = INFINITY;
-    auto argmin = [&](float &best, int &bl) {
-        best = lb, bl = lane;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) { // lanes 16..31 hold +inf
-            const float ob = __shfl_xor_sync(AMPC_FULL_MASK, best, o);
-            const int ol = __shfl_xor_sync(AMPC_FULL_MASK, bl, o);
-            if (ob < best || (ob == best && ol < bl)) best = ob, bl = ol;
-        }
-        best = __shfl_sync(AMPC_FULL_MASK, best, 0);
-        bl = __shfl_sync(AMPC_FULL_MASK, bl, 0);
+    auto argmin = [&](float &best, int &bl) { // nearest live tile, ties to the lowest lane
+        best = warp_argmin_nonneg(lb, lane, bl);
     };
     float best;
     int bl;
@@ -1090,14 +1097,14 @@ knn_search2_kernel(const KnnParams P) {
     double bound = INFINITY;
     for (int c0 = g_begin; c0 < g_end; c0 += KS_GCHUNK) {
         const int cn = min(KS_GCHUNK, g_end - c0);
-        double ubmin = INFINITY;
+        float ubmin = INFINITY;
         for (int j = lane; j < cn; j += 32) {
             const float4 a = knn_ldg(gboxes + 2 * (int64_t)(c0 + j)), h = knn_ldg(gboxes + 2 * (int64_t)(c0 + j) + 1);
             glb[j] = knn_box_lb32(qf, a.x, a.y, a.z, a.w, h.x, h.y);
             if (__float_as_int(h.z) >= k)
-                ubmin = fmin(ubmin, (double)knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y));
+                ubmin = fminf(ubmin, knn_box_ub32(qf, a.x, a.y, a.z, a.w, h.x, h.y));
         }
-        bound = fmin(bound, warp_min(ubmin));
+        bound = fmin(bound, (double)warp_min_nonneg(ubmin));
         __syncwarp();
         for (int pick = 0; pick < KS_GPICKS; ++pick) {
             float best = INFINITY;
@@ -1106,13 +1113,8 @@ knn_search2_kernel(const KnnParams P) {
                 const float v = glb[j];
                 if (v < best) best = v, bj = j; // NaN (visited) never wins
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float ob = __shfl_xor_sync(AMPC_FULL_MASK, best, o);
-                const int oj = __shfl_xor_sync(AMPC_FULL_MASK, bj, o);
-                if (ob < best || (ob == best && oj >= 0 && (bj < 0 || oj < bj))) best = ob, bj = oj;
-            }
-            if (bj < 0 || !((double)best <= bound))
+            best = warp_argmin_nonneg(best, bj < 0 ? 0x7fffffff : bj, bj); // ties to the lowest group
+            if (bj == 0x7fffffff || !((double)best <= bound))
                 break;
             visit_group(P, boxes, tsrc, n, g, gg, c0 + bj, qf, qx, qy, qz, e, bound, k, lane, by_w);
             __syncwarp();
