@@ -1069,7 +1069,7 @@ __device__ __forceinline__ void visit_group(const KnnParams &P, const float4 *bo
 // any group or tile seen that holds at least k points.
 constexpr int KS_GCHUNK = 1024; // group lower bounds kept in shared memory per warp (16384 tiles = 1M points)
 constexpr int KS_GPICKS = 2;
-__global__ void __launch_bounds__(KS_WARPS * 32, 6)
+__global__ void __launch_bounds__(KS_WARPS * 32, 8)
 knn_search2_kernel(const KnnParams P) {
     __shared__ float sGLB[KS_WARPS][KS_GCHUNK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

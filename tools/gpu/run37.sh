@@ -1,0 +1,7 @@
+timeout 900 python -m pytest tests/test_gpu_knn.py tests/test_gpu_round.py -x -q 2>&1 | tail -2
+for L in "" $1; do
+  AMPC_LIB=$L timeout 600 python bench.py --mode knn_sweep --steps 5 2> gpurun_out/b37.err | python -c "
+import json,sys
+k=json.loads([l for l in sys.stdin if l.startswith('{')][-1])
+print('lib=[$L]', ' '.join('%d:%.3f/%.3f' % (r['npts'], r['search_ms'], r['stage_frac']) for r in k['rows']))"
+done
