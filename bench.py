@@ -441,7 +441,39 @@ def run_ours(args):
     # kernels of that step occupy; with one lane that is the kernel's own duration, with several
     # lanes the kernels overlap and the step time is the honest denominator
     solve_busy_ms = solve_ms if L == 1 else (total_ms / args.steps) * solve_ms / (index_ms + knn_ms + solve_ms)
-    solve_tflops = iters_sum * F_ITER / (solve_busy_ms * 1e-3) / 1e12
+    in_step_tflops = iters_sum * F_ITER / (solve_busy_ms * 1e-3) / 1e12
+    # ... and the kernel by itself: the same launches (the packed parameter vectors of the last round,
+    # the same warm starts, one launch per lane in flight as in the step) with nothing else running,
+    # CUDA events around every launch on its stream and around the whole loop
+    def solve_only(rounds):
+        main = torch.cuda.current_stream()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_launch = []
+        torch.cuda.synchronize()
+        e0.record(main)
+        for ln in lanes:
+            ln["st"].wait_event(e0)
+        for _ in range(rounds):
+            for ln in lanes:
+                with torch.cuda.stream(ln["st"]):
+                    ln["w"].copy_(ln["w0"], non_blocking=True)
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(ln["st"])
+                    ln["h"].solve_dev(BL, ln["h"].last_prefix_ptr(), ln["w"], info_dev=ln["info"], stream=ln["st"].cuda_stream)
+                    b.record(ln["st"])
+                    per_launch.append((a, b))
+        for ln in lanes:
+            main.wait_stream(ln["st"])
+        e1.record(main)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in per_launch]
+    solve_only(1)
+    so_rounds = 6
+    so_ms, so_launch = solve_only(so_rounds)
+    info_so, _ = solver_stats(A, torch.cat([ln["info"] for ln in lanes]))
+    so_iters = float(info_so["iters"].astype(np.float64).sum())  # (== iters_sum: same problems, same starts)
+    solve_tflops = so_rounds * so_iters * F_ITER / (so_ms * 1e-3) / 1e12
+    so_launch_ms = sum(so_launch) / len(so_launch)
     step_ms = index_ms + knn_ms + solve_ms
     kern = "ipm_quad_kernel" if BL >= 8192 else "ipm_solve_kernel"
     traffic, traffic_src = ncu_traffic("ipm_quad" if BL >= 8192 else "ipm_solve")
@@ -457,16 +489,27 @@ def run_ours(args):
         "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": "hand-written dependent-FMA-chain kernel on this GPU, this run (ampc_measure_fp64_peak)",
         "work_model": "sum of interior-point iterations x %d FP64 flop (SURVEY.md 8d: (N-1) K 250 + N 4275)" % F_ITER,
-        "iterations_per_step": iters_sum, "avg_launch_ms": solve_ms, "solve_ms_per_step_share_of_timed_region": solve_busy_ms,
+        "measured": "a loop of this kernel alone after the timed region (%d launches of %d instances on the step's inputs, %d in "
+                    "flight on %d streams exactly as in the step): achieved = flops of all launches / CUDA-event time of the loop"
+                    % (so_rounds * L, BL, L, L),
+        "avg_launch_ms": so_launch_ms, "launches_in_flight": L, "iterations_per_launch": so_iters / L,
+        "per_launch": {"flop": so_iters / L * F_ITER, "tflops": so_iters / L * F_ITER / (so_launch_ms * 1e-3) / 1e12,
+                       "frac": so_iters / L * F_ITER / (so_launch_ms * 1e-3) / 1e12 / fp64_peak,
+                       "note": "flops of ONE launch / its own average duration: a lower bound, the launch shares the GPU "
+                               "with the other lane's launch for most of that time"},
+        "in_step": {"iterations_per_step": iters_sum, "avg_launch_ms": solve_ms, "tflops": in_step_tflops,
+                    "frac": in_step_tflops / fp64_peak, "solve_ms_per_step_share_of_timed_region": solve_busy_ms,
+                    "note": "inside the timed region the solve launches overlap the other lane's index / search kernels: "
+                            "step time x this kernel's share of the summed stage times as the denominator"},
         "step_share": solve_ms / step_ms,
-        "measured": "CUDA events around the kernel on its stream inside the timed region",
         # the HBM-bound part, from the single-batch pass (its kernels run alone there; with several
         # lanes in flight a kernel's event time includes time-sharing with the other lane's kernels)
         "cloud_index": {"kernel": "cloud_index_kernel (+ compaction check + group boxes)", "bound": "hbm",
                         "achieved": B * b_knn / (single["stage_ms"]["index"] * 1e-3) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s",
                         "frac": B * b_knn / (single["stage_ms"]["index"] * 1e-3) / 1e9 / hbm_peak,
-                        "traffic": idx_traffic, "peak_source": hbm_src, "algorithmic_bytes_per_launch": B * b_knn,
+                        "traffic": None if idx_traffic is None else idx_traffic * B / 32768.0,  # (captured on a 32768-scene launch)
+                        "peak_source": hbm_src, "algorithmic_bytes_per_launch": B * b_knn,
                         "as_laid_out_16B_GBps": B * 16 * npts / (single["stage_ms"]["index"] * 1e-3) / 1e9,
                         "avg_launch_ms": single["stage_ms"]["index"], "instances_per_launch": B,
                         "step_share": index_ms / step_ms},
