@@ -91,6 +91,8 @@ struct ampc_handle {
     int smem_per_sm = 228 * 1024;
     int quad_warps_per_sm = 8; // AMPC_QUAD_WARPS_PER_SM (255 registers per thread allow 8)
     int quad_per_warp = 0;     // AMPC_QUADS_PER_WARP (1, 2, 4, 8): 0 = by batch size
+    int quad_cta_warps = 2;    // AMPC_QUAD_CTA_WARPS: warps per CTA of the quad kernel (they meet once per pass; measured
+                               // at 32768 instances, solve-only TFLOP/s: 1: 2.47, 2: 2.59, 3: 2.53, 6: 2.36)
     int solve_kernel = 0;      // AMPC_SOLVE_KERNEL: 0 auto (by batch size), 1 warp, 2 quad
     int quad_min_batch = 8192; // AMPC_QUAD_MIN_BATCH: smallest batch the quad kernel takes in auto mode
     int solve_smem_set[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -641,6 +643,12 @@ int launch_solve_quad(ampc_handle *h, int B, const double *prefix_dev, double *w
     const int cap = h->n_sm * per_sm; // resident warps
     int warps = (B + Q - 1) / Q;
     if (warps > cap) warps = cap;
+    // warps per CTA (AMPC_QUAD_CTA_WARPS): only when the machine is full anyway; whole CTAs per SM
+    int cw = 1;
+    if (warps == cap && h->quad_cta_warps > 1) {
+        cw = h->quad_cta_warps < per_sm ? h->quad_cta_warps : per_sm;
+        while (per_sm % cw) --cw;
+    }
     const size_t smem = quad_smem_bytes(h->cfg.N, Q);
     {
         // the attribute belongs to the function, not to the handle: only ever raise it
@@ -648,12 +656,12 @@ int launch_solve_quad(ampc_handle *h, int B, const double *prefix_dev, double *w
         static int set_to[64][4] = {{0}};
         std::lock_guard<std::mutex> g(mtx);
         const int dev = h->cfg.device & 63;
-        if ((int)smem > set_to[dev][qs]) {
+        if ((int)(smem * cw) > set_to[dev][qs]) {
             const void *fn = qs == 0 ? (const void *)ipm_quad_kernel<0>
                            : qs == 1 ? (const void *)ipm_quad_kernel<1>
                            : qs == 2 ? (const void *)ipm_quad_kernel<2> : (const void *)ipm_quad_kernel<3>;
-            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            set_to[dev][qs] = (int)smem;
+            CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem * cw)));
+            set_to[dev][qs] = (int)(smem * cw);
         }
     }
     const size_t need = (size_t)warps * quad_ws_bytes_per_warp(h->cfg.N, Q);
@@ -684,11 +692,12 @@ int launch_solve_quad(ampc_handle *h, int B, const double *prefix_dev, double *w
         CK(cudaGetLastError());
         order = ord;
     }
+    const int grid = (warps + cw - 1) / cw;
     switch (qs) {
-    case 0: ipm_quad_kernel<0><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
-    case 1: ipm_quad_kernel<1><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
-    case 2: ipm_quad_kernel<2><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
-    default: ipm_quad_kernel<3><<<warps, 32, smem, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    case 0: ipm_quad_kernel<0><<<grid, 32 * cw, smem * cw, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    case 1: ipm_quad_kernel<1><<<grid, 32 * cw, smem * cw, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    case 2: ipm_quad_kernel<2><<<grid, 32 * cw, smem * cw, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
+    default: ipm_quad_kernel<3><<<grid, 32 * cw, smem * cw, st>>>(h->consts, B, prefix_dev, w_dev, info_dev, active, order, wsp, cnt); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -803,6 +812,10 @@ int ampc_create(const ampc_config *cfg, ampc_handle **out) {
     if (const char *e = std::getenv("AMPC_QUADS_PER_WARP")) {
         const int v = std::atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) h->quad_per_warp = v;
+    }
+    if (const char *e = std::getenv("AMPC_QUAD_CTA_WARPS")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 8) h->quad_cta_warps = v;
     }
     if (const char *e = std::getenv("AMPC_QUAD_WARPS_PER_SM")) {
         const int v = std::atoi(e);

@@ -832,22 +832,26 @@ enum { QS_DONE = 0, QS_FETCH, QS_TEST, QS_FACTOR, QS_TRIAL, QS_FINISH };
 
 // One CTA = one warp = up to Q = 1 << QS instances in flight, refilled from *counter.
 template <int QS>
-__global__ void __launch_bounds__(32, 1)
+__global__ void __launch_bounds__(256, 1)
 ipm_quad_kernel(const __grid_constant__ SolveConsts c, int B, const double *__restrict__ prefix,
                 double *__restrict__ w_inout, SolveOut *__restrict__ info,
                 const int32_t *__restrict__ active /* nullable: instances with 0 are skipped */,
                 const int32_t *__restrict__ order /* nullable: the order instances are taken in */,
                 double *__restrict__ ws, int32_t *__restrict__ counter) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    constexpr int Q = 1 << QS;
+    // a CTA is W independent warps (own shared-memory slice, own workspace, own queue slots) that
+    // only meet at one barrier per pass, so that they run the same phase -- the same code -- together
+    const int wid = threadIdx.x >> 5, gw = blockIdx.x * (blockDim.x >> 5) + wid;
+    unsigned char *smem_raw = smem_all + (size_t)wid * quad_smem_bytes(c.N, Q);
     QuadTables *tb = reinterpret_cast<QuadTables *>(smem_raw);
     double *Sw = reinterpret_cast<double *>(smem_raw + ((sizeof(QuadTables) + 15) & ~(size_t)15));
-    constexpr int Q = 1 << QS;
-    const int lane = threadIdx.x, a = lane & 3;
+    const int lane = threadIdx.x & 31, a = lane & 3;
     const int sq = (lane >> 2) & (Q - 1); // lanes of quads >= Q shadow a live quad, all effects off
     const bool live = (lane >> 2) < Q;
     const int N = c.N, n_w = 10 + 14 * N;
     const QuadGmem LG(N);
-    double *Gw = ws + (size_t)blockIdx.x * LG.total * Q;
+    double *Gw = ws + (size_t)gw * LG.total * Q;
     double *S = Sw + sq, *G = Gw + sq; // this quad's column
     if (lane < 4) {
         tb->ch[lane] = c.ch[lane];
@@ -1000,6 +1004,9 @@ ipm_quad_kernel(const __grid_constant__ SolveConsts c, int B, const double *__re
         { // ---- next instance from the queue
             const bool in_fetch = state == QS_FETCH;
             if (QANY(in_fetch)) {
+                // the lanes of an idle quad ran this pass's sweeps with their effects off: order their
+                // (discarded) reads of the multiplier rows before the new instance's values land there
+                __syncwarp();
                 int b = B;
                 if (in_fetch && a == 0) {
                     for (;;) {
@@ -1119,8 +1126,12 @@ ipm_quad_kernel(const __grid_constant__ SolveConsts c, int B, const double *__re
         __syncwarp();
         const unsigned req = __ballot_sync(AMPC_FULL_MASK, want && a == 0 && live);
         const unsigned alive = __ballot_sync(AMPC_FULL_MASK, state != QS_DONE);
-        if (alive == 0u)
+        if (blockDim.x == 32) {
+            if (alive == 0u)
+                break;
+        } else if (__syncthreads_and(alive == 0u)) { // (a finished warp keeps meeting the others: its passes are empty)
             break;
+        }
         const int m = __popc(req);
         const int n_items = m * N;
         // item i = (stage i / m, i-th requesting quad); stage-major so that neighbouring lanes read

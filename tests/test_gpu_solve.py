@@ -143,8 +143,8 @@ def test_solve_matches_512_independent_optima():
 def test_quad_kernel_refill_and_packing_do_not_change_results(monkeypatch):
     """The quad kernel's results must not depend on how instances share warps: 1, 2, 4 or 8
     instances per warp, with and without refill from the queue (one resident warp per SM and
-    2 instances per warp -> 296 slots for 400 instances), bit for bit; and they must agree with
-    the warp-per-instance kernel to rounding."""
+    2 instances per warp -> 296 slots for 400 instances), one or two warps per CTA, bit for
+    bit; and they must agree with the warp-per-instance kernel to rounding."""
     N, K, B = 20, 16, 400
     inst = make_instances([500 + (b % 40) for b in range(B)], N, K, 10000)
     rng = np.random.default_rng(7)
@@ -159,7 +159,12 @@ def test_quad_kernel_refill_and_packing_do_not_change_results(monkeypatch):
                       ("q4", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "4"}),
                       ("q1", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "1"}),
                       ("q2_refill", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "2",
-                                     "AMPC_QUAD_WARPS_PER_SM": "1"})]:
+                                     "AMPC_QUAD_WARPS_PER_SM": "1"}),
+                      # two warps per CTA meeting once per pass (the default for full machines), with refill
+                      ("q1_cta2", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "1",
+                                   "AMPC_QUAD_WARPS_PER_SM": "2", "AMPC_QUAD_CTA_WARPS": "2"}),
+                      ("q1_cta1", {"AMPC_SOLVE_KERNEL": "quad", "AMPC_QUADS_PER_WARP": "1",
+                                   "AMPC_QUAD_WARPS_PER_SM": "2", "AMPC_QUAD_CTA_WARPS": "1"})]:
         for k_, v_ in env.items():
             monkeypatch.setenv(k_, v_)
         h = A.Handle(N=N, K=K, max_batch=B, max_points=16)
@@ -167,8 +172,9 @@ def test_quad_kernel_refill_and_packing_do_not_change_results(monkeypatch):
         h.close()
         monkeypatch.delenv("AMPC_QUADS_PER_WARP", raising=False)
         monkeypatch.delenv("AMPC_QUAD_WARPS_PER_SM", raising=False)
+        monkeypatch.delenv("AMPC_QUAD_CTA_WARPS", raising=False)
     W8, i8 = results["q8"]
-    for name in ("q4", "q1", "q2_refill"):
+    for name in ("q4", "q1", "q2_refill", "q1_cta2", "q1_cta1"):
         W, info = results[name]
         assert (W == W8).all(), name
         for f in ("cost", "iters", "status", "n_reg", "n_backtrack"):
