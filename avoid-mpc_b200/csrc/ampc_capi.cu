@@ -520,9 +520,14 @@ int launch_knn(ampc_handle *h, int kind, int B, const int32_t *scene_of_dev, con
     const dim3 grid(B, (Q + KS_WARPS - 1) / KS_WARPS, segs);
     if (grid.y > 65535u)
         return fail(h, AMPC_ERR_UNSUPPORTED, "too many queries per instance");
-    if (h->knn_two_level)
-        knn_search2_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
-    else
+    if (h->knn_two_level) {
+        // group lower bounds per warp: what a slot of this handle can need, at most KS_GCHUNK
+        int gch = (int)((h->slot_groups[kind] + 31) / 32 * 32);
+        if (gch > KS_GCHUNK) gch = KS_GCHUNK;
+        if (gch < 32) gch = 32;
+        P.gchunk = gch;
+        knn_search2_kernel<<<grid, KS_WARPS * 32, (size_t)KS_WARPS * gch * sizeof(float), st>>>(P);
+    } else
         knn_search_kernel<<<grid, KS_WARPS * 32, 0, st>>>(P);
     h->launches++;
     CK(cudaGetLastError());

@@ -135,6 +135,7 @@ struct KnnParams {
     const float4 *sorted;    // Morton-bucketed copies (x, y, z, original index) of the scenes whose layout is -1
     const float4 *boxes;     // slot s at boxes + s*slot_tiles*2 (two float4 per tile)
     const float4 *gboxes;    // slot s at gboxes + s*slot_groups*2 (two float4 per group of tiles)
+    int gchunk;              // group lower bounds kept in shared memory per warp (<= KS_GCHUNK, multiple of 32)
     int64_t slot_groups;
     const int32_t *counts;   // points held in each slot (after the NaN filter)
     int64_t slot_points;
@@ -1071,7 +1072,7 @@ constexpr int KS_GCHUNK = 1024; // group lower bounds kept in shared memory per 
 constexpr int KS_GPICKS = 2;
 __global__ void __launch_bounds__(KS_WARPS * 32, 8)
 knn_search2_kernel(const KnnParams P) {
-    __shared__ float sGLB[KS_WARPS][KS_GCHUNK];
+    extern __shared__ float sGLB_all[]; // KS_WARPS x P.gchunk group lower bounds
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = blockIdx.y * KS_WARPS + warp, b = blockIdx.x, seg = blockIdx.z;
     if (q >= P.Q || (P.active && P.active[b] == 0))
@@ -1091,12 +1092,12 @@ knn_search2_kernel(const KnnParams P) {
     const GroupGeom gg(g);
     const int per = (gg.n_groups + P.segs - 1) / P.segs;
     const int g_begin = seg * per, g_end = min(gg.n_groups, g_begin + per);
-    float *glb = sGLB[warp];
+    float *glb = sGLB_all + warp * P.gchunk;
     const QueryF qf = make_queryf(qx, qy, qz);
     TopK e{INFINITY, 0xffffffffu};
     double bound = INFINITY;
-    for (int c0 = g_begin; c0 < g_end; c0 += KS_GCHUNK) {
-        const int cn = min(KS_GCHUNK, g_end - c0);
+    for (int c0 = g_begin; c0 < g_end; c0 += P.gchunk) {
+        const int cn = min(P.gchunk, g_end - c0);
         float ubmin = INFINITY;
         for (int j = lane; j < cn; j += 32) {
             const float4 a = knn_ldg(gboxes + 2 * (int64_t)(c0 + j)), h = knn_ldg(gboxes + 2 * (int64_t)(c0 + j) + 1);
