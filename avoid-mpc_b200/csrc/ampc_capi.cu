@@ -625,7 +625,7 @@ int launch_solve_w(ampc_handle *h, int B, const double *prefix_dev, double *w_de
     return AMPC_OK;
 }
 
-// Quad kernel (ipm_quad.cuh): persistent one-warp CTAs with Q = 1, 2, 4 or 8 instances in flight
+// Quad kernel (ipm_quad.cuh): persistent warps (one or two per CTA) with Q = 1, 2, 4 or 8 instances in flight
 // per warp.  Shared memory per warp grows with Q (and N), registers allow 8 warps per SM.
 int quad_warps_per_sm(const ampc_handle *h, int Q) {
     const size_t smem = quad_smem_bytes(h->cfg.N, Q) + 1024; // + the per-CTA reservation
