@@ -23,6 +23,14 @@
 #include <mutex>
 #include <vector>
 
+// -DAMPC_WITH_ROS in a catkin build: AddVertex also takes the reference's own argument types
+#if defined(AMPC_WITH_ROS) && __has_include(<sensor_msgs/Image.h>) && __has_include(<Eigen/Dense>)
+#include <sensor_msgs/Image.h>
+#include <sensor_msgs/image_encodings.h>
+#include <stdexcept>
+#define AMPC_HAVE_ROS_TYPES 1
+#endif
+
 using Mat4 = std::array<double, 16>; // row-major homogeneous transform
 Mat4 Mat4Identity();
 
@@ -50,6 +58,25 @@ public:
     using CloudPtr = pcl::PointCloud<pcl::PointXYZ>::Ptr;
     // AddVertex (:36-53): a frame whose Obstacle cloud comes out empty is dropped (:41-43)
     void AddVertex(const Mat4 &Twb, const DepthImage &depth);
+#ifdef AMPC_HAVE_ROS_TYPES
+    // the reference's signature (include/FrameKDMap.h:61-62).  The message buffer is handed over as it
+    // is (the reference copies it through cv_bridge::toCvCopy, src/FrameKDMap.cpp:94); CV_16UC1 and
+    // CV_32FC1 are the two types ProcessDepth accepts (:96-103)
+    void AddVertex(const Eigen::Matrix4d &mat4Twb, const sensor_msgs::ImageConstPtr &depth) {
+        namespace enc = sensor_msgs::image_encodings;
+        Mat4 T;
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c)
+                T[4 * r + c] = mat4Twb(r, c);
+        DepthImage d;
+        d.data = depth->data.data();
+        d.rows = (int)depth->height, d.cols = (int)depth->width, d.step = depth->step;
+        d.isU16 = depth->encoding == enc::TYPE_16UC1 || depth->encoding == enc::MONO16;
+        if (!d.isU16 && depth->encoding != enc::TYPE_32FC1)
+            throw std::runtime_error("FrameKDMap::AddVertex: depth image must be 16UC1 or 32FC1");
+        AddVertex(T, d);
+    }
+#endif
     // the two InitializeNew calls + swap into mCurFrame (:44-51) for ready-made clouds; Twc = Twb * Tbc
     void AddClouds(const CloudPtr &cloud, const CloudPtr &edgeCloud, const Mat4 &Twc = Mat4Identity(),
                    int rowWidthHint = 0);
