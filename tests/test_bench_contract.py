@@ -53,3 +53,14 @@ def test_gpu_arm_needs_a_gpu():
     r = _run(["--steps", "1"])
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_cpu_c0_mode_runs_without_a_gpu():
+    """BASELINE config C0 (one instance, K = 8, 10k points, one thread) is a CPU measurement: the
+    mode must work on a box without a GPU and report per-stage p50 / p90."""
+    r = _run(["--mode", "cpu_c0"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert d["mode"] == "cpu_c0" and d["unit"] == "ms" and d["converged_frac"] == 1.0
+    for k in ("tree_build", "knn_20x8", "nlp_solve", "total"):
+        assert 0 < d[k]["p50"] <= d[k]["p90"]
